@@ -1,0 +1,305 @@
+"""Benchmark of the denoise hot path (BASELINE.json metric: TSP-500 graphs/sec, 50-step categorical).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+A "step" = one pass of the hot path over one batch: the full 50-step categorical denoise of
+16 TSP-500 (k=50) instances batched block-diagonally in one call (BASELINE config[1]), per GPU.
+Weak scaling: every rank owns its own batch; no collective inside the loop; for N > 1 the final
+heatmaps are all-gathered over NCCL inside the timed region (north_star).
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_NODES, KNN, BATCH, DENOISE_STEPS, T = 500, 50, 16, 50, 1000
+H, L = 256, 12
+METRIC = "TSP-500 graphs/sec, 50-step categorical denoise"
+UNIT = "graphs/s"
+
+
+def model_args():
+  from types import SimpleNamespace as NS
+  return NS(diffusion_type="categorical", diffusion_schedule="linear", diffusion_steps=T, sparse_factor=KNN,
+            n_layers=L, hidden_dim=H, aggregation="sum", parallel_sampling=1, sequential_sampling=1,
+            inference_schedule="cosine", inference_diffusion_steps=DENOISE_STEPS, inference_trick="ddim")
+
+
+def workload_config(n_gpus):
+  return {"workload": f"TSP-{N_NODES} sparse k={KNN}, categorical diffusion, {DENOISE_STEPS} denoise steps, "
+                      f"batch {BATCH} instances per GPU in one block-diagonal call (BASELINE configs[1])",
+          "nodes_per_graph": N_NODES, "knn": KNN, "batch_per_gpu": BATCH, "denoise_steps": DENOISE_STEPS,
+          "global_batch": BATCH * n_gpus, "parallelism": f"dp{n_gpus} (independent batches, no in-loop collective)",
+          "weights": "seeded random init of the reference architecture (12 layers, hidden 256), per_layer_out de-zeroed",
+          "l2_policy": "working set (edge stream 410 MB/GPU) exceeds the 126 MB L2; no explicit flush needed"}
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+  """nvidia-smi clocks + throttle reasons sampled during the timed region."""
+  Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+       "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+       "clocks_event_reasons.sw_power_cap")
+
+  def __init__(self, gpu_index):
+    self.idx, self.rows, self.proc = gpu_index, [], None
+
+  def start(self):
+    try:
+      self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                    "-i", str(self.idx), "-lms", "200"], stdout=subprocess.PIPE,
+                                   stderr=subprocess.DEVNULL, text=True)
+      self.th = threading.Thread(target=self._read, daemon=True)
+      self.th.start()
+    except Exception:
+      self.proc = None
+
+  def _read(self):
+    for line in self.proc.stdout:
+      self.rows.append([x.strip() for x in line.split(",")])
+
+  def stop(self):
+    if not self.proc:
+      return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+    self.proc.terminate()
+    try:
+      self.proc.wait(timeout=2)
+    except Exception:
+      self.proc.kill()
+    sm, mx, reasons = [], [], set()
+    for r in self.rows:
+      try:
+        sm.append(float(r[1])); mx.append(float(r[2]))
+      except Exception:
+        continue
+      for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+        if v.lower().startswith("active"):
+          reasons.add(name)
+    return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+            "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+  p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+  if os.path.exists(p):
+    d = json.load(open(p))
+    return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, sustained copy)"
+  return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic():
+  p = os.path.join(ROOT, "profiles", "edge_kernel_traffic.json")
+  if os.path.exists(p):
+    try:
+      return json.load(open(p)).get("dram_bytes_per_launch")
+    except Exception:
+      return None
+  return None
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_oracle_graphs_per_s(denoise_steps_sample, threads=None):
+  """The oracle port (oracle/difusco_oracle.py, torch CPU) on ONE TSP-500 k=50 instance for
+  `denoise_steps_sample` of the 50 denoise steps, all host threads; extrapolated to 50 steps."""
+  import torch
+  from difusco_b200 import synthetic as syn
+  from oracle import difusco_oracle as orc
+  torch.set_num_threads(threads or os.cpu_count())
+  w = orc.Weights(syn.make_encoder_weights(0, out_channels=2))
+  pts, ei = syn.tsp_sparse_batch(N_NODES, KNN, 1, seed=1234)
+  xt0 = (syn.initial_noise(ei.shape[1], 0) > 0).astype(np.float32)
+  sched = orc.inference_schedule("cosine", T, DENOISE_STEPS)
+  _, Qbar = orc.categorical_tables(T, "linear")
+  xt = torch.from_numpy(xt0)
+  ei_t = torch.from_numpy(ei)
+  with torch.no_grad():
+    orc.encoder_forward_sparse_tsp(w, pts, xt, torch.tensor([1000.0]), ei_t)   # warm-up forward
+    t0 = time.perf_counter()
+    for (t1, t2) in sched[:denoise_steps_sample]:
+      out = orc.encoder_forward_sparse_tsp(w, pts, xt, torch.tensor([float(t1)]), ei_t)
+      _, xt = orc.categorical_posterior(Qbar, t1, t2, out.softmax(-1), xt)
+    dt = time.perf_counter() - t0
+  per_graph = dt * DENOISE_STEPS / denoise_steps_sample
+  return 1.0 / per_graph, dt, torch.get_num_threads()
+
+
+def run_reference(args, rank, world):
+  """--impl reference: the reference's CPU path (oracle port; the reference is Python and its
+  dependencies torch_sparse / lightning are not installable here) on the host cores."""
+  if rank != 0:
+    return
+  sample = 10
+  for _ in range(max(args.warmup, 0)):
+    pass   # CPU path: warm-up forward is inside cpu_oracle_graphs_per_s
+  vals, secs = [], 0.0
+  for _ in range(args.steps):
+    v, dt, threads = cpu_oracle_graphs_per_s(sample)
+    vals.append(v); secs += dt
+  value = float(np.mean(vals))
+  line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+          "warmup": args.warmup, "ms_per_step": 1000.0 / value * BATCH, "higher_is_better": True,
+          "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+          "config": workload_config(args.gpus),
+          "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                           "sample": f"1 TSP-500 k=50 instance, {sample} of {DENOISE_STEPS} denoise steps per "
+                                     f"timed step, extrapolated x{DENOISE_STEPS // sample}; torch CPU fp32"},
+          "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+          "gpu_launches": 0}
+  print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+  import torch
+  import torch.distributed as dist
+  from difusco_b200 import _cabi, synthetic as syn
+  from difusco_b200.pl_tsp_model import TSPModel
+
+  torch.cuda.set_device(local_rank)
+  dev = torch.device("cuda", local_rank)
+  if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+  model = TSPModel(model_args())
+  w = syn.make_encoder_weights(0, out_channels=2)
+  model.model.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()})
+  model.cuda(local_rank).eval()
+  if os.environ.get("DFB_EDGE_IMPL", "tc") == "fp32":
+    model.model.engine().set_edge_impl(_cabi.EDGE_IMPL_FP32)
+
+  # per-rank batch: different instances on every rank (seed offset), same shape
+  pts, ei = syn.tsp_sparse_batch(N_NODES, KNN, BATCH, seed=1234 + 1000 * rank)
+  V, E = pts.shape[0], ei.shape[1]
+  xt0 = (syn.initial_noise(E, rank) > 0).astype(np.float32)
+  d_pts, d_ei, d_xt0 = torch.from_numpy(pts).to(dev), torch.from_numpy(ei).to(dev), torch.from_numpy(xt0).to(dev)
+  ctx = model.model.engine()
+  stream = torch.cuda.current_stream().cuda_stream
+
+  from difusco_b200.utils.diffusion_schedulers import InferenceSchedule
+  sched = InferenceSchedule("cosine", T, DENOISE_STEPS)
+  t1s, cs, ls = [], [], []
+  for i in range(DENOISE_STEPS):
+    t1, t2 = sched(i)
+    c, last = model.posterior_consts(int(t1), int(t2))
+    t1s.append(int(t1)); cs.append(c); ls.append(last)
+
+  model._prepare(d_pts, d_ei, dev)
+  gathered = [torch.empty(E, device=dev) for _ in range(world)] if world > 1 else None
+  x = torch.empty(E, device=dev)
+
+  def one_step(seed):
+    x.copy_(d_xt0)
+    ctx.denoise(_cabi.CATEGORICAL, x.data_ptr(), t1s, cs, ls, None, seed, stream)
+    if world > 1:
+      dist.all_gather(gathered, x)
+
+  def fence():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  for i in range(args.warmup):
+    one_step(i)
+  fence()
+  sampler = ClockSampler(local_rank)
+  if rank == 0:
+    sampler.start()
+  launches0 = ctx.launch_count()
+  ctx.profile_begin()
+  ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  ev0.record()
+  for i in range(args.steps):
+    one_step(100 + i)
+  ev1.record()
+  fence()
+  ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+  edge_ms, edge_n = ctx.profile_end()
+  launches = ctx.launch_count() - launches0
+  clocks = sampler.stop() if rank == 0 else None
+  if world > 1:
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+  total_ms = float(ms.item())
+  hm = x.cpu().numpy()
+  assert np.isfinite(hm).all() and hm.min() >= 0.0 and hm.max() <= 1.0 + 1e-5
+
+  # ---- e2e: same metric through the host-buffer C-ABI call (H2D of inputs + D2H of the heatmap per step)
+  p_pts = torch.from_numpy(pts).pin_memory()
+  p_ei = torch.from_numpy(ei).pin_memory()
+  p_xt0 = torch.from_numpy(xt0).pin_memory()
+  p_hm = torch.empty(E, dtype=torch.float32).pin_memory()
+
+  def e2e_step(seed):
+    ctx.denoise_host(_cabi.CATEGORICAL, p_pts.data_ptr(), p_ei.data_ptr(), V, E, 1, p_xt0.data_ptr(), t1s, cs, ls,
+                     seed, p_hm.data_ptr(), stream)
+  e2e_step(0)
+  fence()
+  t0 = time.perf_counter()
+  for i in range(args.steps):
+    e2e_step(200 + i)
+  fence()
+  e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
+  if world > 1:
+    dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+  e2e_value = BATCH * world * args.steps / float(e2e_s.item())
+  h2d = pts.nbytes + ei.nbytes + xt0.nbytes
+  d2h = p_hm.numel() * 4
+
+  if rank == 0:
+    value = BATCH * world * args.steps / (total_ms / 1e3)
+    peak, peak_src = measured_peaks()
+    # algorithmic bytes per fused edge-layer launch: E*H*4 write every layer, E*H*4 read for
+    # layers 1..L-1 (layer 0 reads the 2-row LUT); the head's read of the last e is booked to the head kernel.
+    alg_bytes_total = (2 * L - 1) * E * H * 4 * DENOISE_STEPS * args.steps
+    achieved = alg_bytes_total / (edge_ms / 1e3) / 1e9 if edge_ms > 0 else 0.0
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 (3-term bf16 split on tcgen05, fp32 accumulate)",
+            "data": "synthetic", "config": workload_config(world),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
+                         "kernel": "k_edge_layer_tc" if os.environ.get("DFB_EDGE_IMPL", "tc") != "fp32" else "k_edge_layer_fp32",
+                         "algorithmic_bytes_per_launch": (2 * L - 1) * E * H * 4 / L,
+                         "launches_timed": int(edge_n), "kernel_ms_total": edge_ms,
+                         "kernel_share_of_step": edge_ms / total_ms},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches), "clocks": clocks}
+    if world == 1 and not args.no_cpu_baseline:
+      v, dt, threads = cpu_oracle_graphs_per_s(20)
+      line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                              "sample": f"oracle port (torch CPU fp32) on 1 TSP-500 k=50 instance, 20 of "
+                                        f"{DENOISE_STEPS} denoise steps ({dt:.1f} s), extrapolated x2.5"}
+    print(json.dumps(line))
+  if world > 1:
+    dist.destroy_process_group()
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument("--gpus", type=int, default=1)
+  ap.add_argument("--steps", type=int, default=3)
+  ap.add_argument("--warmup", type=int, default=3)
+  ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+  ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+  args = ap.parse_args()
+  rank = int(os.environ.get("RANK", "0"))
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+  if args.impl == "reference":
+    run_reference(args, rank, world)
+    return
+  if world != args.gpus and world == 1 and args.gpus > 1:
+    raise SystemExit("launch with torchrun for --gpus > 1 (one process per GPU)")
+  run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+  main()

@@ -1,0 +1,806 @@
+// C-ABI of difusco_b200 (include/difusco_b200.h): context, weight packing, graph preparation and
+// the orchestration of one forward / one denoise step / the whole denoise loop.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/difusco_b200.h"
+#include "common.cuh"
+#include "edge_layer_fp32.cuh"
+#include "edge_layer_tc.cuh"
+#include "kernels_small.cuh"
+
+using namespace dfb;
+
+static std::string g_create_error;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+struct dfb_ctx {
+  int device = 0;
+  std::string err;
+  // ---- model ----
+  bool weights_loaded = false;
+  int L = 0, out_channels = 0, node_only = 0;
+  int agg_mode = AGG_SUM;
+  int edge_impl = DFB_EDGE_IMPL_TC;
+  DevBuf wbuf, wbuf16, layers_dev;
+  std::vector<LayerParams> layers;
+  TimeParams tp{};
+  HeadParams hp{};
+  const float *Wt_node = nullptr, *b_node = nullptr, *Wt_edge = nullptr, *b_edge = nullptr;
+  const float *dimt128 = nullptr, *dimt256 = nullptr;
+  float* lut = nullptr;   // [2][256] categorical edge-embedding LUT (inside wbuf)
+  // ---- graph ----
+  bool graph_ready = false, points_ready = false;
+  GraphDev g{};
+  int gn_segments = 1;
+  DevBuf d_row, d_col, d_perm, d_rowptr, d_grp_first, d_grp_pair, d_ei_stage;
+  // ---- workspace ----
+  DevBuf e, h, h0, uvab, uvab0, partials, feat, tvec, tvals, gn_part, gn_stats, d_points, d_xt, d_u;
+  int tvec_steps_cap = 0;
+  // ---- accounting ----
+  int64_t launches = 0;
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  TcState tc;
+};
+
+#define FAIL(ctx, code, ...)                         \
+  do {                                               \
+    char _b[512];                                    \
+    snprintf(_b, sizeof(_b), __VA_ARGS__);           \
+    (ctx)->err = _b;                                 \
+    return (code);                                   \
+  } while (0)
+
+#define CK(ctx, call)                                                                       \
+  do {                                                                                      \
+    cudaError_t _e = (call);                                                                \
+    if (_e != cudaSuccess)                                                                  \
+      FAIL(ctx, DFB_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+#define CKL(ctx)                                                                           \
+  do {                                                                                      \
+    (ctx)->launches++;                                                                      \
+    cudaError_t _e = cudaGetLastError();                                                    \
+    if (_e != cudaSuccess)                                                                  \
+      FAIL(ctx, DFB_E_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+static int ensure(dfb_ctx* ctx, DevBuf& b, size_t bytes) {
+  if (bytes <= b.cap) return DFB_OK;
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+  size_t want = bytes + (bytes >> 3);   // slack so slightly larger graphs do not reallocate
+  cudaError_t e = cudaMalloc(&b.p, want);
+  if (e != cudaSuccess) {
+    e = cudaMalloc(&b.p, bytes);
+    want = bytes;
+  }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    FAIL(ctx, DFB_E_NOMEM, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+  }
+  b.cap = want;
+  return DFB_OK;
+}
+#define ENS(ctx, buf, bytes)                     \
+  do {                                           \
+    int _r = ensure(ctx, buf, bytes);            \
+    if (_r) return _r;                           \
+  } while (0)
+
+static bool is_device_ptr(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// ================================================================================================
+extern "C" int dfb_abi_version(void) { return DFB_ABI_VERSION; }
+
+extern "C" const char* dfb_last_error(const dfb_ctx* ctx) {
+  return ctx ? ctx->err.c_str() : g_create_error.c_str();
+}
+
+extern "C" int dfb_create(dfb_ctx** out, int device) {
+  if (!out) return DFB_E_INVALID;
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                     " (difusco_b200 has no CPU fallback)";
+    cudaGetLastError();
+    return DFB_E_CUDA;
+  }
+  if (device < 0 || device >= n) {
+    g_create_error = "device index out of range";
+    return DFB_E_INVALID;
+  }
+  if ((e = cudaSetDevice(device)) != cudaSuccess) {
+    g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+    return DFB_E_CUDA;
+  }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  if (prop.major != 10) {
+    char b[160];
+    snprintf(b, sizeof(b), "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
+             prop.major, prop.minor);
+    g_create_error = b;
+    return DFB_E_UNSUPPORTED;
+  }
+  dfb_ctx* ctx = new dfb_ctx();
+  ctx->device = device;
+  e = cudaFuncSetAttribute(k_edge_layer_fp32, cudaFuncAttributeMaxDynamicSharedMemorySize, EF_SMEM);
+  if (e != cudaSuccess) {
+    g_create_error = std::string("cudaFuncSetAttribute(fp32 edge kernel): ") + cudaGetErrorString(e);
+    delete ctx;
+    return DFB_E_CUDA;
+  }
+  int r = tc_init(&ctx->tc, prop.multiProcessorCount);
+  if (r != 0) {
+    g_create_error = "tcgen05 edge kernel setup failed: " + ctx->tc.err;
+    delete ctx;
+    return DFB_E_CUDA;
+  }
+  *out = ctx;
+  return DFB_OK;
+}
+
+extern "C" int dfb_destroy(dfb_ctx* ctx) {
+  if (!ctx) return DFB_OK;
+  cudaSetDevice(ctx->device);
+  DevBuf* bufs[] = {&ctx->wbuf, &ctx->wbuf16, &ctx->layers_dev, &ctx->d_row, &ctx->d_col, &ctx->d_perm,
+                    &ctx->d_rowptr, &ctx->d_grp_first, &ctx->d_grp_pair, &ctx->d_ei_stage, &ctx->e, &ctx->h,
+                    &ctx->h0, &ctx->uvab, &ctx->uvab0, &ctx->partials, &ctx->feat, &ctx->tvec, &ctx->tvals,
+                    &ctx->gn_part, &ctx->gn_stats, &ctx->d_points, &ctx->d_xt, &ctx->d_u};
+  for (DevBuf* b : bufs)
+    if (b->p) cudaFree(b->p);
+  for (cudaEvent_t ev : ctx->ev_pool) cudaEventDestroy(ev);
+  tc_destroy(&ctx->tc);
+  delete ctx;
+  return DFB_OK;
+}
+
+extern "C" int dfb_set_edge_impl(dfb_ctx* ctx, int impl) {
+  if (!ctx) return DFB_E_INVALID;
+  if (impl != DFB_EDGE_IMPL_TC && impl != DFB_EDGE_IMPL_FP32) FAIL(ctx, DFB_E_INVALID, "unknown edge impl %d", impl);
+  ctx->edge_impl = impl;
+  return DFB_OK;
+}
+
+extern "C" int64_t dfb_launch_count(const dfb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ================================================================================================
+// weights
+// ================================================================================================
+static uint16_t f2bf16_rn(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+  uint32_t r = u + 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(r >> 16);
+}
+static float bf16_to_f(uint16_t h) {
+  uint32_t u = (uint32_t)h << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+extern "C" int dfb_load_weights(dfb_ctx* ctx, int n_layers, int hidden_dim, int out_channels,
+                                int node_feature_only, int n_tensors, const char* const* names,
+                                const float* const* tensors, const int64_t* numels) {
+  if (!ctx) return DFB_E_INVALID;
+  CK(ctx, cudaSetDevice(ctx->device));
+  if (hidden_dim != H) FAIL(ctx, DFB_E_UNSUPPORTED, "hidden_dim %d: kernels are specialised for 256", hidden_dim);
+  if (n_layers < 1 || n_layers > 64) FAIL(ctx, DFB_E_INVALID, "n_layers %d out of range", n_layers);
+  if (out_channels != 1 && out_channels != 2) FAIL(ctx, DFB_E_INVALID, "out_channels must be 1 or 2");
+  std::map<std::string, std::pair<const float*, int64_t>> sd;
+  for (int i = 0; i < n_tensors; ++i) {
+    std::string k = names[i];
+    if (k.rfind("model.", 0) == 0) k = k.substr(6);
+    sd[k] = {tensors[i], numels[i]};
+  }
+  auto get = [&](const std::string& k, int64_t n, const float** out) -> int {
+    auto it = sd.find(k);
+    if (it == sd.end()) FAIL(ctx, DFB_E_INVALID, "state_dict key '%s' missing", k.c_str());
+    if (it->second.second != n)
+      FAIL(ctx, DFB_E_INVALID, "state_dict key '%s' has %lld elements, expected %lld", k.c_str(),
+           (long long)it->second.second, (long long)n);
+    *out = it->second.first;
+    return DFB_OK;
+  };
+#define GET(k, n, out)                 \
+  do {                                 \
+    int _r = get(k, n, out);           \
+    if (_r) return _r;                 \
+  } while (0)
+
+  const int L = n_layers;
+  // ---- fp32 arena layout ----
+  std::vector<float> arena;
+  auto put = [&](size_t n) {
+    size_t off = arena.size();
+    arena.resize(off + ((n + 63) / 64) * 64, 0.0f);   // 256-byte aligned slots
+    return off;
+  };
+  auto put_T = [&](const float* W, int out_f, int in_f) {   // [out][in] -> in-major [in][out]
+    size_t off = put((size_t)out_f * in_f);
+    for (int o = 0; o < out_f; ++o)
+      for (int i = 0; i < in_f; ++i) arena[off + (size_t)i * out_f + o] = W[(size_t)o * in_f + i];
+    return off;
+  };
+  auto put_v = [&](const float* v, int n) {
+    size_t off = put(n);
+    memcpy(&arena[off], v, n * sizeof(float));
+    return off;
+  };
+  struct LOff {
+    size_t Wt_uvab, b_uvab, Wt_C, Wt_O, b_O, hg, hb, eg, eb, og, ob, Wt_tau, b_tau;
+  };
+  std::vector<LOff> lo(L);
+  std::vector<uint16_t> arena16((size_t)L * 4 * H * H);
+  const float* p;
+  for (int l = 0; l < L; ++l) {
+    std::string pre = "layers." + std::to_string(l) + ".";
+    const float *W[4], *b[4], *WC, *bC;
+    const char* nm[4] = {"U", "V", "A", "B"};
+    for (int q = 0; q < 4; ++q) {
+      GET(pre + nm[q] + ".weight", H * H, &W[q]);
+      GET(pre + nm[q] + ".bias", H, &b[q]);
+    }
+    GET(pre + "C.weight", H * H, &WC);
+    GET(pre + "C.bias", H, &bC);
+    lo[l].Wt_uvab = put((size_t)H * 4 * H);
+    lo[l].b_uvab = put(4 * H);
+    for (int q = 0; q < 4; ++q) {
+      for (int o = 0; o < H; ++o) {
+        for (int i = 0; i < H; ++i) arena[lo[l].Wt_uvab + (size_t)i * 4 * H + q * H + o] = W[q][(size_t)o * H + i];
+        arena[lo[l].b_uvab + q * H + o] = b[q][o] + (q == 3 ? bC[o] : 0.0f);
+      }
+    }
+    lo[l].Wt_C = put_T(WC, H, H);
+    GET(pre + "norm_h.weight", H, &p); lo[l].hg = put_v(p, H);
+    GET(pre + "norm_h.bias", H, &p);   lo[l].hb = put_v(p, H);
+    GET(pre + "norm_e.weight", H, &p); lo[l].eg = put_v(p, H);
+    GET(pre + "norm_e.bias", H, &p);   lo[l].eb = put_v(p, H);
+    std::string po = "per_layer_out." + std::to_string(l) + ".";
+    const float* WO;
+    GET(po + "0.weight", H, &p); lo[l].og = put_v(p, H);
+    GET(po + "0.bias", H, &p);   lo[l].ob = put_v(p, H);
+    GET(po + "2.weight", H * H, &WO); lo[l].Wt_O = put_T(WO, H, H);
+    GET(po + "2.bias", H, &p);   lo[l].b_O = put_v(p, H);
+    std::string pt = "time_embed_layers." + std::to_string(l) + ".1.";
+    GET(pt + "weight", H * TE, &p); lo[l].Wt_tau = put_T(p, H, TE);
+    GET(pt + "bias", H, &p);        lo[l].b_tau = put_v(p, H);
+    // bf16 hi/lo split of C and O, [out][in] K-major (the tensor-core B operand)
+    uint16_t* a16 = &arena16[(size_t)l * 4 * H * H];
+    for (int i = 0; i < H * H; ++i) {
+      uint16_t hi = f2bf16_rn(WC[i]);
+      a16[i] = hi;
+      a16[H * H + i] = f2bf16_rn(WC[i] - bf16_to_f(hi));
+      hi = f2bf16_rn(WO[i]);
+      a16[2 * H * H + i] = hi;
+      a16[3 * H * H + i] = f2bf16_rn(WO[i] - bf16_to_f(hi));
+    }
+  }
+  size_t o_node_W, o_node_b, o_edge_W, o_edge_b, o_t0W, o_t0b, o_t2W, o_t2b, o_gng, o_gnb, o_outW, o_outb;
+  GET("node_embed.weight", H * H, &p); o_node_W = put_T(p, H, H);
+  GET("node_embed.bias", H, &p);       o_node_b = put_v(p, H);
+  GET("edge_embed.weight", H * H, &p); o_edge_W = put_T(p, H, H);
+  GET("edge_embed.bias", H, &p);       o_edge_b = put_v(p, H);
+  GET("time_embed.0.weight", TE * H, &p); o_t0W = put_T(p, TE, H);
+  GET("time_embed.0.bias", TE, &p);       o_t0b = put_v(p, TE);
+  GET("time_embed.2.weight", TE * TE, &p); o_t2W = put_T(p, TE, TE);
+  GET("time_embed.2.bias", TE, &p);        o_t2b = put_v(p, TE);
+  GET("out.0.weight", H, &p); o_gng = put_v(p, H);
+  GET("out.0.bias", H, &p);   o_gnb = put_v(p, H);
+  GET("out.2.weight", out_channels * H, &p); o_outW = put_v(p, out_channels * H);
+  GET("out.2.bias", out_channels, &p);       o_outb = put_v(p, out_channels);
+
+  // frequency tables: computed by the Python host with the reference's own torch expressions and
+  // passed as pseudo-tensors when available (bit-identical tables); otherwise computed here.
+  size_t o_freqs = put(TE), o_d128 = put(TE), o_d256 = put(H), o_lut = put(2 * H);
+  auto it = sd.find("__const.time_freqs");
+  for (int m = 0; m < TE; ++m)
+    arena[o_freqs + m] = (it != sd.end() && it->second.second == TE)
+                             ? it->second.first[m]
+                             : expf((-9.210340371976184f * (float)m) / (float)TE);
+  it = sd.find("__const.dimt_pos");
+  for (int m = 0; m < TE; ++m)
+    arena[o_d128 + m] = (it != sd.end() && it->second.second == TE)
+                            ? it->second.first[m]
+                            : powf(10000.0f, (2.0f * (float)(m / 2)) / (float)TE);
+  it = sd.find("__const.dimt_scalar");
+  for (int m = 0; m < H; ++m)
+    arena[o_d256 + m] = (it != sd.end() && it->second.second == H)
+                            ? it->second.first[m]
+                            : powf(10000.0f, (2.0f * (float)(m / 2)) / (float)H);
+
+  ENS(ctx, ctx->wbuf, arena.size() * sizeof(float));
+  ENS(ctx, ctx->wbuf16, arena16.size() * sizeof(uint16_t));
+  ENS(ctx, ctx->layers_dev, L * sizeof(LayerParams));
+  CK(ctx, cudaMemcpy(ctx->wbuf.p, arena.data(), arena.size() * sizeof(float), cudaMemcpyHostToDevice));
+  CK(ctx, cudaMemcpy(ctx->wbuf16.p, arena16.data(), arena16.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+  const float* base = (const float*)ctx->wbuf.p;
+  const uint16_t* base16 = (const uint16_t*)ctx->wbuf16.p;
+  ctx->layers.resize(L);
+  for (int l = 0; l < L; ++l) {
+    LayerParams& lp = ctx->layers[l];
+    lp.Wt_uvab = base + lo[l].Wt_uvab; lp.b_uvab = base + lo[l].b_uvab;
+    lp.Wt_C = base + lo[l].Wt_C; lp.Wt_O = base + lo[l].Wt_O; lp.b_O = base + lo[l].b_O;
+    lp.ln_h_g = base + lo[l].hg; lp.ln_h_b = base + lo[l].hb;
+    lp.ln_e_g = base + lo[l].eg; lp.ln_e_b = base + lo[l].eb;
+    lp.ln_o_g = base + lo[l].og; lp.ln_o_b = base + lo[l].ob;
+    lp.Wt_tau = base + lo[l].Wt_tau; lp.b_tau = base + lo[l].b_tau;
+    lp.C_hi = base16 + (size_t)l * 4 * H * H; lp.C_lo = lp.C_hi + H * H;
+    lp.O_hi = lp.C_hi + 2 * H * H;            lp.O_lo = lp.C_hi + 3 * H * H;
+  }
+  CK(ctx, cudaMemcpy(ctx->layers_dev.p, ctx->layers.data(), L * sizeof(LayerParams), cudaMemcpyHostToDevice));
+  ctx->Wt_node = base + o_node_W; ctx->b_node = base + o_node_b;
+  ctx->Wt_edge = base + o_edge_W; ctx->b_edge = base + o_edge_b;
+  ctx->tp.freqs = base + o_freqs; ctx->tp.Wt0 = base + o_t0W; ctx->tp.b0 = base + o_t0b;
+  ctx->tp.Wt2 = base + o_t2W;     ctx->tp.b2 = base + o_t2b;
+  ctx->hp.gn_g = base + o_gng; ctx->hp.gn_b = base + o_gnb; ctx->hp.W = base + o_outW; ctx->hp.b = base + o_outb;
+  ctx->hp.out_channels = out_channels;
+  ctx->dimt128 = base + o_d128; ctx->dimt256 = base + o_d256;
+  ctx->lut = (float*)ctx->wbuf.p + o_lut;
+  ctx->L = L; ctx->out_channels = out_channels; ctx->node_only = node_feature_only;
+
+  int r = tc_bind_weights(&ctx->tc, ctx->layers.data(), L);
+  if (r) FAIL(ctx, DFB_E_CUDA, "tensor-map setup failed: %s", ctx->tc.err.c_str());
+
+  // categorical edge-embedding LUT: edge_embed(edge_pos_embed(x)) for x in {0, 1}
+  if (!node_feature_only) {
+    ENS(ctx, ctx->feat, (size_t)LIN_ROWS * H * sizeof(float));
+    float x01[2] = {0.0f, 1.0f};
+    ENS(ctx, ctx->tvals, 4096 * sizeof(float));
+    CK(ctx, cudaMemcpy(ctx->tvals.p, x01, sizeof(x01), cudaMemcpyHostToDevice));
+    k_scalar_features<<<2, H>>>((const float*)ctx->tvals.p, nullptr, ctx->dimt256, (float*)ctx->feat.p, 2);
+    CKL(ctx);
+    k_linear<<<dim3(1, 1), 256>>>((const float*)ctx->feat.p, ctx->Wt_edge, ctx->b_edge, ctx->lut, 2, H);
+    CKL(ctx);
+    CK(ctx, cudaDeviceSynchronize());
+  }
+  ctx->weights_loaded = true;
+  ctx->points_ready = false;
+  return DFB_OK;
+}
+
+extern "C" int dfb_set_aggregation(dfb_ctx* ctx, int mode) {
+  if (!ctx) return DFB_E_INVALID;
+  if (mode < AGG_SUM || mode > AGG_MAX) FAIL(ctx, DFB_E_INVALID, "unknown aggregation %d", mode);
+  ctx->agg_mode = mode;
+  return DFB_OK;
+}
+
+// ================================================================================================
+// graph
+// ================================================================================================
+extern "C" int dfb_prepare_graph(dfb_ctx* ctx, const int64_t* edge_index, int64_t V64, int64_t E64,
+                                 int gn_segments, void* stream_) {
+  if (!ctx) return DFB_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream_;
+  CK(ctx, cudaSetDevice(ctx->device));
+  if (!ctx->weights_loaded) FAIL(ctx, DFB_E_INVALID, "dfb_load_weights must be called first");
+  if (V64 <= 0 || E64 <= 0 || V64 > 0x7fffffff / 4 || E64 > 0x7ffffff0)
+    FAIL(ctx, DFB_E_INVALID, "bad graph size V=%lld E=%lld", (long long)V64, (long long)E64);
+  const int V = (int)V64, E = (int)E64;
+  if (gn_segments < 1) FAIL(ctx, DFB_E_INVALID, "gn_segments must be >= 1");
+  {
+    int R = ctx->node_only ? V : E;
+    if (R % gn_segments) FAIL(ctx, DFB_E_INVALID, "gn_segments %d does not divide %d rows", gn_segments, R);
+  }
+  std::vector<int64_t> stage;
+  const int64_t* ei = edge_index;
+  if (is_device_ptr(edge_index)) {
+    stage.resize((size_t)2 * E);
+    CK(ctx, cudaMemcpyAsync(stage.data(), edge_index, (size_t)2 * E * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CK(ctx, cudaStreamSynchronize(st));
+    ei = stage.data();
+  }
+  const int64_t* row64 = ei;
+  const int64_t* col64 = ei + E;
+  std::vector<int> rowptr((size_t)V + 1, 0);
+  bool sorted = true;
+  for (int s = 0; s < E; ++s) {
+    int64_t r = row64[s], c = col64[s];
+    if (r < 0 || r >= V || c < 0 || c >= V)
+      FAIL(ctx, DFB_E_INVALID, "edge %d = (%lld,%lld) out of range for %d nodes", s, (long long)r, (long long)c, V);
+    rowptr[(size_t)r + 1]++;
+    if (s && r < row64[s - 1]) sorted = false;
+  }
+  for (int i = 0; i < V; ++i) rowptr[i + 1] += rowptr[i];
+  std::vector<int> row(E), col(E), perm;
+  if (sorted) {
+    for (int s = 0; s < E; ++s) {
+      row[s] = (int)row64[s];
+      col[s] = (int)col64[s];
+    }
+  } else {   // stable counting sort by row
+    perm.resize(E);
+    std::vector<int> cur(rowptr.begin(), rowptr.end() - 1);
+    for (int s = 0; s < E; ++s) {
+      int pos = cur[row64[s]]++;
+      perm[pos] = s;
+      row[pos] = (int)row64[s];
+      col[pos] = (int)col64[s];
+    }
+  }
+  const int nG = (E + GROUP - 1) / GROUP;
+  std::vector<int> gfirst(nG), gpair((size_t)nG + 1);
+  int np = 0;
+  for (int gI = 0; gI < nG; ++gI) {
+    int s0 = gI * GROUP, s1 = std::min(E, s0 + GROUP) - 1;
+    gfirst[gI] = row[s0];
+    gpair[gI] = np;
+    np += row[s1] - row[s0] + 1;
+  }
+  gpair[nG] = np;
+
+  ENS(ctx, ctx->d_row, (size_t)E * 4);
+  ENS(ctx, ctx->d_col, (size_t)E * 4);
+  ENS(ctx, ctx->d_rowptr, ((size_t)V + 1) * 4);
+  ENS(ctx, ctx->d_grp_first, (size_t)nG * 4);
+  ENS(ctx, ctx->d_grp_pair, ((size_t)nG + 1) * 4);
+  CK(ctx, cudaMemcpyAsync(ctx->d_row.p, row.data(), (size_t)E * 4, cudaMemcpyHostToDevice, st));
+  CK(ctx, cudaMemcpyAsync(ctx->d_col.p, col.data(), (size_t)E * 4, cudaMemcpyHostToDevice, st));
+  CK(ctx, cudaMemcpyAsync(ctx->d_rowptr.p, rowptr.data(), ((size_t)V + 1) * 4, cudaMemcpyHostToDevice, st));
+  CK(ctx, cudaMemcpyAsync(ctx->d_grp_first.p, gfirst.data(), (size_t)nG * 4, cudaMemcpyHostToDevice, st));
+  CK(ctx, cudaMemcpyAsync(ctx->d_grp_pair.p, gpair.data(), ((size_t)nG + 1) * 4, cudaMemcpyHostToDevice, st));
+  if (!sorted) {
+    ENS(ctx, ctx->d_perm, (size_t)E * 4);
+    CK(ctx, cudaMemcpyAsync(ctx->d_perm.p, perm.data(), (size_t)E * 4, cudaMemcpyHostToDevice, st));
+  }
+  CK(ctx, cudaStreamSynchronize(st));   // host vectors go out of scope
+  GraphDev& g = ctx->g;
+  g.V = V; g.E = E;
+  g.row = (const int*)ctx->d_row.p; g.col = (const int*)ctx->d_col.p;
+  g.perm = sorted ? nullptr : (const int*)ctx->d_perm.p;
+  g.rowptr = (const int*)ctx->d_rowptr.p;
+  g.n_groups = nG; g.grp_first = (const int*)ctx->d_grp_first.p; g.grp_pair = (const int*)ctx->d_grp_pair.p;
+  g.n_pairs = np;
+  ctx->gn_segments = gn_segments;
+
+  // workspace
+  const size_t Epad = (size_t)((E + 127) / 128) * 128;   // whole 128-row tiles for the tensor-core kernel
+  ENS(ctx, ctx->e, Epad * H * sizeof(float));
+  ENS(ctx, ctx->h, (size_t)V * H * sizeof(float));
+  ENS(ctx, ctx->h0, (size_t)V * H * sizeof(float));
+  ENS(ctx, ctx->uvab, (size_t)V * 4 * H * sizeof(float));
+  ENS(ctx, ctx->uvab0, (size_t)V * 4 * H * sizeof(float));
+  ENS(ctx, ctx->partials, (size_t)np * H * sizeof(float));
+  const size_t feat_rows = 65536;
+  ENS(ctx, ctx->feat, feat_rows * H * sizeof(float));
+  {
+    int R = ctx->node_only ? V : E;
+    int rps = R / gn_segments;
+    int bps = (rps + GN_ROWS_PER_BLOCK - 1) / GN_ROWS_PER_BLOCK;
+    ENS(ctx, ctx->gn_part, (size_t)gn_segments * bps * 32 * 2 * sizeof(double));
+    ENS(ctx, ctx->gn_stats, (size_t)gn_segments * 32 * 2 * sizeof(float));
+  }
+  ENS(ctx, ctx->d_xt, (size_t)std::max(V, E) * sizeof(float));
+  ctx->graph_ready = true;
+  ctx->points_ready = false;
+  return DFB_OK;
+}
+
+// rows X[R][256] -> Y = X Wt + b through the generic linear, chunked features
+static int linear_rows(dfb_ctx* ctx, const float* X, const float* Wt, const float* b, float* Y, int R, int N,
+                       cudaStream_t st) {
+  dim3 grid((R + LIN_ROWS - 1) / LIN_ROWS, N / 256);
+  k_linear<<<grid, 256, 0, st>>>(X, Wt, b, Y, R, N);
+  CKL(ctx);
+  return DFB_OK;
+}
+
+extern "C" int dfb_set_points(dfb_ctx* ctx, const float* points, void* stream_) {
+  if (!ctx) return DFB_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream_;
+  CK(ctx, cudaSetDevice(ctx->device));
+  if (!ctx->graph_ready) FAIL(ctx, DFB_E_INVALID, "dfb_prepare_graph must be called first");
+  if (ctx->node_only) FAIL(ctx, DFB_E_INVALID, "dfb_set_points is for the TSP encoder (node_feature_only=0)");
+  const int V = ctx->g.V;
+  const float* dp = points;
+  if (!is_device_ptr(points)) {
+    ENS(ctx, ctx->d_points, (size_t)V * 2 * sizeof(float));
+    CK(ctx, cudaMemcpyAsync(ctx->d_points.p, points, (size_t)V * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
+    dp = (const float*)ctx->d_points.p;
+  }
+  const int CH = 65536;
+  for (int v0 = 0; v0 < V; v0 += CH) {
+    int n = std::min(CH, V - v0);
+    k_pos_features<<<n, H, 0, st>>>(dp + (size_t)v0 * 2, ctx->dimt128, (float*)ctx->feat.p, n);
+    CKL(ctx);
+    int r = linear_rows(ctx, (const float*)ctx->feat.p, ctx->Wt_node, ctx->b_node,
+                        (float*)ctx->h0.p + (size_t)v0 * H, n, H, st);
+    if (r) return r;
+  }
+  // layer 0's node linears are step-invariant too
+  int r = linear_rows(ctx, (const float*)ctx->h0.p, ctx->layers[0].Wt_uvab, ctx->layers[0].b_uvab,
+                      (float*)ctx->uvab0.p, V, 4 * H, st);
+  if (r) return r;
+  ctx->points_ready = true;
+  return DFB_OK;
+}
+
+// ================================================================================================
+// one forward (+ optional fused posterior)
+// ================================================================================================
+static int launch_edge_layer(dfb_ctx* ctx, int l, const float* uvab, const float* tvec_edge, int write_e,
+                             int e_zero, const float* xt_for_lut, cudaStream_t st) {
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (ctx->profiling) {
+    if (ctx->ev_used + 2 > ctx->ev_pool.size()) {
+      for (int i = 0; i < 256; ++i) {
+        cudaEvent_t ev;
+        CK(ctx, cudaEventCreate(&ev));
+        ctx->ev_pool.push_back(ev);
+      }
+    }
+    ev0 = ctx->ev_pool[ctx->ev_used++];
+    ev1 = ctx->ev_pool[ctx->ev_used++];
+    CK(ctx, cudaEventRecord(ev0, st));
+  }
+  if (ctx->edge_impl == DFB_EDGE_IMPL_FP32) {
+    if (e_zero) CK(ctx, cudaMemsetAsync(ctx->e.p, 0, (size_t)ctx->g.E * H * sizeof(float), st));
+    if (xt_for_lut) {
+      k_lut_expand<<<(ctx->g.E + 3) / 4, 256, 0, st>>>(xt_for_lut, ctx->g.perm, ctx->lut, (float*)ctx->e.p, ctx->g.E);
+      CKL(ctx);
+    }
+    k_edge_layer_fp32<<<ctx->g.n_groups, 256, EF_SMEM, st>>>((float*)ctx->e.p, uvab, (float*)ctx->partials.p,
+                                                            ctx->g, ctx->layers[l], tvec_edge, write_e,
+                                                            ctx->agg_mode);
+    CKL(ctx);
+  } else {
+    int r = tc_launch_edge_layer(&ctx->tc, l, (float*)ctx->e.p, uvab, (float*)ctx->partials.p, ctx->g,
+                                 ctx->layers[l], tvec_edge, write_e, e_zero, xt_for_lut, ctx->lut,
+                                 ctx->agg_mode, st);
+    if (r) FAIL(ctx, r == -3 ? DFB_E_UNSUPPORTED : DFB_E_CUDA, "tcgen05 edge layer: %s", ctx->tc.err.c_str());
+    ctx->launches += ctx->tc.last_launches;
+  }
+  if (ctx->profiling) CK(ctx, cudaEventRecord(ev1, st));
+  return DFB_OK;
+}
+
+// tvec: [L][256] for this step.  binary_xt: xt in {0,1} guaranteed (categorical denoise state).
+static int run_forward(dfb_ctx* ctx, const float* xt, const float* tvec, bool binary_xt, PosteriorArgs pa,
+                       cudaStream_t st) {
+  const GraphDev& g = ctx->g;
+  const int V = g.V, E = g.E, L = ctx->L;
+  float* h = (float*)ctx->h.p;
+  float* e = (float*)ctx->e.p;
+  float* uvab = (float*)ctx->uvab.p;
+  const float* xt_lut = nullptr;
+  int e_zero = 0;
+  if (!ctx->node_only) {
+    if (!ctx->points_ready) FAIL(ctx, DFB_E_INVALID, "dfb_set_points must be called before a TSP forward");
+    CK(ctx, cudaMemcpyAsync(h, ctx->h0.p, (size_t)V * H * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (binary_xt) {
+      xt_lut = xt;   // layer 0 reads the 2-row LUT instead of a materialised e0
+    } else {         // general values (Gaussian diffusion): e0 = edge_embed(edge_pos_embed(xt))
+      const int CH = 65536;
+      for (int s0 = 0; s0 < E; s0 += CH) {
+        int n = std::min(CH, E - s0);
+        // with a permutation the index array addresses the whole xt; without, offset the input
+        k_scalar_features<<<n, H, 0, st>>>(g.perm ? xt : xt + s0, g.perm ? g.perm + s0 : nullptr, ctx->dimt256,
+                                           (float*)ctx->feat.p, n);
+        CKL(ctx);
+        int r = linear_rows(ctx, (const float*)ctx->feat.p, ctx->Wt_edge, ctx->b_edge, e + (size_t)s0 * H, n, H, st);
+        if (r) return r;
+      }
+    }
+  } else {
+    const int CH = 65536;
+    for (int v0 = 0; v0 < V; v0 += CH) {
+      int n = std::min(CH, V - v0);
+      k_scalar_features<<<n, H, 0, st>>>(xt + v0, nullptr, ctx->dimt256, (float*)ctx->feat.p, n);
+      CKL(ctx);
+      int r = linear_rows(ctx, (const float*)ctx->feat.p, ctx->Wt_node, ctx->b_node, h + (size_t)v0 * H, n, H, st);
+      if (r) return r;
+    }
+    e_zero = 1;   // gnn_encoder.py:407: e0 = zeros
+  }
+  for (int l = 0; l < L; ++l) {
+    const float* uv = uvab;
+    if (l == 0 && !ctx->node_only) {
+      uv = (const float*)ctx->uvab0.p;
+    } else {
+      int r = linear_rows(ctx, h, ctx->layers[l].Wt_uvab, ctx->layers[l].b_uvab, uvab, V, 4 * H, st);
+      if (r) return r;
+    }
+    const float* tv = tvec + (size_t)l * H;
+    int write_e = !(ctx->node_only && l == L - 1);
+    int r = launch_edge_layer(ctx, l, uv, ctx->node_only ? nullptr : tv, write_e, (l == 0) ? e_zero : 0,
+                              (l == 0) ? xt_lut : nullptr, st);
+    if (r) return r;
+    if (ctx->node_only || l < L - 1) {   // TSP never reads h after the last layer (gnn_encoder.py:400)
+      k_node_update<<<(V + 7) / 8, 256, 0, st>>>(h, uv, (const float*)ctx->partials.p, g, ctx->layers[l].ln_h_g,
+                                                 ctx->layers[l].ln_h_b, ctx->node_only ? tv : nullptr);
+      CKL(ctx);
+    }
+  }
+  // head
+  const float* Z = ctx->node_only ? h : e;
+  const int R = ctx->node_only ? V : E;
+  const int rps = R / ctx->gn_segments;
+  const int bps = (rps + GN_ROWS_PER_BLOCK - 1) / GN_ROWS_PER_BLOCK;
+  k_gn_partial<<<dim3(bps, ctx->gn_segments), 256, 0, st>>>(Z, rps, (double*)ctx->gn_part.p);
+  CKL(ctx);
+  k_gn_final<<<ctx->gn_segments, 32, 0, st>>>((const double*)ctx->gn_part.p, bps, rps, (float*)ctx->gn_stats.p);
+  CKL(ctx);
+  k_head<<<(R + 7) / 8, 256, 0, st>>>(Z, R, rps, (const float*)ctx->gn_stats.p, ctx->node_only ? nullptr : g.perm,
+                                      ctx->hp, pa);
+  CKL(ctx);
+  return DFB_OK;
+}
+
+static int compute_tvecs(dfb_ctx* ctx, const float* tvals_host, int S, cudaStream_t st) {
+  ENS(ctx, ctx->tvals, std::max<size_t>(4096, (size_t)S) * sizeof(float));
+  ENS(ctx, ctx->tvec, (size_t)S * ctx->L * H * sizeof(float));
+  CK(ctx, cudaMemcpyAsync(ctx->tvals.p, tvals_host, (size_t)S * sizeof(float), cudaMemcpyHostToDevice, st));
+  k_time_vectors<<<S, 256, 0, st>>>((const float*)ctx->tvals.p, ctx->tp, (const LayerParams*)ctx->layers_dev.p,
+                                    ctx->L, (float*)ctx->tvec.p);
+  CKL(ctx);
+  return DFB_OK;
+}
+
+extern "C" int dfb_encoder_forward(dfb_ctx* ctx, const float* xt, float t, float* out, void* stream_) {
+  if (!ctx) return DFB_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream_;
+  CK(ctx, cudaSetDevice(ctx->device));
+  if (!ctx->graph_ready) FAIL(ctx, DFB_E_INVALID, "dfb_prepare_graph must be called first");
+  int r = compute_tvecs(ctx, &t, 1, st);
+  if (r) return r;
+  CK(ctx, cudaStreamSynchronize(st));   // &t is a stack address
+  PosteriorArgs pa{};
+  pa.mode = HEAD_FORWARD;
+  pa.net_out = out;
+  return run_forward(ctx, xt, (const float*)ctx->tvec.p, false, pa, st);
+}
+
+static int step_args(dfb_ctx* ctx, int diffusion_type, const float* consts, int last, PosteriorArgs* pa) {
+  if (diffusion_type == DFB_DIFFUSION_CATEGORICAL) {
+    if (ctx->out_channels != 2) FAIL(ctx, DFB_E_INVALID, "categorical diffusion needs out_channels == 2");
+    pa->mode = HEAD_CATEGORICAL;
+  } else if (diffusion_type == DFB_DIFFUSION_GAUSSIAN) {
+    if (ctx->out_channels != 1) FAIL(ctx, DFB_E_INVALID, "gaussian diffusion needs out_channels == 1");
+    pa->mode = HEAD_GAUSSIAN;
+  } else {
+    FAIL(ctx, DFB_E_INVALID, "Unknown diffusion type %d", diffusion_type);
+  }
+  for (int i = 0; i < 4; ++i) pa->c[i] = consts[i];
+  pa->last = last;
+  return DFB_OK;
+}
+
+extern "C" int dfb_denoise_step(dfb_ctx* ctx, int diffusion_type, const float* xt_in, float t,
+                                const float* consts, int last, const float* uniforms, uint64_t seed,
+                                int step_index, float* xt_out, float* p_out, float* net_out, void* stream_) {
+  if (!ctx) return DFB_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream_;
+  CK(ctx, cudaSetDevice(ctx->device));
+  if (!ctx->graph_ready) FAIL(ctx, DFB_E_INVALID, "dfb_prepare_graph must be called first");
+  PosteriorArgs pa{};
+  int r = step_args(ctx, diffusion_type, consts, last, &pa);
+  if (r) return r;
+  r = compute_tvecs(ctx, &t, 1, st);
+  if (r) return r;
+  CK(ctx, cudaStreamSynchronize(st));
+  pa.xt_in = xt_in; pa.uniforms = uniforms; pa.seed = seed; pa.step = (unsigned)step_index;
+  pa.xt_out = xt_out; pa.p_out = p_out; pa.net_out = net_out;
+  return run_forward(ctx, xt_in, (const float*)ctx->tvec.p, diffusion_type == DFB_DIFFUSION_CATEGORICAL, pa, st);
+}
+
+extern "C" int dfb_denoise(dfb_ctx* ctx, int diffusion_type, float* xt, int steps, const int32_t* t1,
+                           const float* consts, const int32_t* last_flags, const float* uniforms,
+                           uint64_t seed, void* stream_) {
+  if (!ctx) return DFB_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream_;
+  CK(ctx, cudaSetDevice(ctx->device));
+  if (!ctx->graph_ready) FAIL(ctx, DFB_E_INVALID, "dfb_prepare_graph must be called first");
+  if (steps < 1 || steps > 4096) FAIL(ctx, DFB_E_INVALID, "steps %d out of range", steps);
+  std::vector<float> tv(steps);
+  for (int i = 0; i < steps; ++i) tv[i] = (float)t1[i];
+  int r = compute_tvecs(ctx, tv.data(), steps, st);
+  if (r) return r;
+  CK(ctx, cudaStreamSynchronize(st));   // tv is a local; one sync before the loop, none inside
+  const size_t N = ctx->node_only ? ctx->g.V : ctx->g.E;
+  for (int i = 0; i < steps; ++i) {
+    PosteriorArgs pa{};
+    r = step_args(ctx, diffusion_type, consts + 4 * i, last_flags[i], &pa);
+    if (r) return r;
+    pa.xt_in = xt; pa.xt_out = xt;
+    pa.uniforms = uniforms ? uniforms + (size_t)i * N : nullptr;
+    pa.seed = seed; pa.step = (unsigned)i;
+    r = run_forward(ctx, xt, (const float*)ctx->tvec.p + (size_t)i * ctx->L * H,
+                    diffusion_type == DFB_DIFFUSION_CATEGORICAL, pa, st);
+    if (r) return r;
+  }
+  return DFB_OK;
+}
+
+extern "C" int dfb_denoise_host(dfb_ctx* ctx, int diffusion_type, const float* points,
+                                const int64_t* edge_index, int64_t V, int64_t E, int gn_segments,
+                                const float* xt0, int steps, const int32_t* t1, const float* consts,
+                                const int32_t* last_flags, uint64_t seed, float* heatmap_out, void* stream_) {
+  if (!ctx) return DFB_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream_;
+  CK(ctx, cudaSetDevice(ctx->device));
+  int r = dfb_prepare_graph(ctx, edge_index, V, E, gn_segments, st);
+  if (r) return r;
+  if (!ctx->node_only) {
+    if (!points) FAIL(ctx, DFB_E_INVALID, "points required for TSP");
+    r = dfb_set_points(ctx, points, st);
+    if (r) return r;
+  }
+  const size_t N = ctx->node_only ? (size_t)V : (size_t)E;
+  CK(ctx, cudaMemcpyAsync(ctx->d_xt.p, xt0, N * sizeof(float), cudaMemcpyHostToDevice, st));
+  r = dfb_denoise(ctx, diffusion_type, (float*)ctx->d_xt.p, steps, t1, consts, last_flags, nullptr, seed, st);
+  if (r) return r;
+  CK(ctx, cudaMemcpyAsync(heatmap_out, ctx->d_xt.p, N * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CK(ctx, cudaStreamSynchronize(st));
+  return DFB_OK;
+}
+
+// ================================================================================================
+extern "C" int dfb_profile_begin(dfb_ctx* ctx) {
+  if (!ctx) return DFB_E_INVALID;
+  ctx->profiling = true;
+  ctx->ev_used = 0;
+  return DFB_OK;
+}
+extern "C" int dfb_profile_end(dfb_ctx* ctx, double* ms, int64_t* n) {
+  if (!ctx) return DFB_E_INVALID;
+  CK(ctx, cudaSetDevice(ctx->device));
+  CK(ctx, cudaDeviceSynchronize());
+  double tot = 0.0;
+  for (size_t i = 0; i + 1 < ctx->ev_used; i += 2) {
+    float t = 0.f;
+    CK(ctx, cudaEventElapsedTime(&t, ctx->ev_pool[i], ctx->ev_pool[i + 1]));
+    tot += t;
+  }
+  if (ms) *ms = tot;
+  if (n) *n = (int64_t)(ctx->ev_used / 2);
+  ctx->profiling = false;
+  ctx->ev_used = 0;
+  return DFB_OK;
+}
+
+// ================================================================================================
+// Test hook: run only GEMM1 of layer `layer` (acc = e_in * C^T, split-bf16 on tensor cores) on the
+// prepared graph's tiling and dump the TMEM accumulator.  Isolates descriptors / TMA / TMEM
+// plumbing from the epilogue math in tests/test_tc_gemm.py.
+extern "C" int dfb_debug_edge_gemm(dfb_ctx* ctx, int layer, const float* e_in, float* acc_out, void* stream_) {
+  if (!ctx) return DFB_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream_;
+  CK(ctx, cudaSetDevice(ctx->device));
+  if (!ctx->graph_ready) FAIL(ctx, DFB_E_INVALID, "dfb_prepare_graph must be called first");
+  if (layer < 0 || layer >= ctx->L) FAIL(ctx, DFB_E_INVALID, "layer out of range");
+  ctx->tc.debug_acc = acc_out;
+  int r = tc_launch_edge_layer(&ctx->tc, layer, const_cast<float*>(e_in), (const float*)ctx->uvab.p,
+                               (float*)ctx->partials.p, ctx->g, ctx->layers[layer], nullptr, 0, 0, nullptr,
+                               ctx->lut, AGG_SUM, st);
+  ctx->tc.debug_acc = nullptr;
+  if (r) FAIL(ctx, DFB_E_CUDA, "tcgen05 edge layer: %s", ctx->tc.err.c_str());
+  ctx->launches += 1;
+  return DFB_OK;
+}

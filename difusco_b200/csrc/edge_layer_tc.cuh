@@ -1,0 +1,592 @@
+// The hot kernel: one fused GNN edge layer on 5th-gen tensor cores (tcgen05 + TMEM + TMA), sm_100a.
+//
+//   e_hat = C e + A h[col] + B h[row]                         gnn_encoder.py:104,110
+//   agg  += sigmoid(e_hat) * V h[col]   (row-segment sums)     :112,163,177-191
+//   e_til = relu(LN_e(e_hat)) + tau                            :131,135,445
+//   e     = e + O silu(LN_O(e_til)) + b_O   (in place)         :449, :339-347
+//
+// Persistent CTAs, one per SM, each looping over 128-edge tiles (edges are row-sorted).
+// Warp roles (192 threads):
+//   warp 0      TMA producer: streams the bf16 hi/lo weight K-chunks (L2 -> smem, 128B swizzle)
+//   warp 1      MMA issuer  : one thread issues tcgen05.mma (M=128, N=256, K=16), owns TMEM alloc
+//   warps 2..5  row workers : thread == edge row == TMEM lane.  They convert the fp32 edge tile to
+//               bf16 hi/lo A-operand chunks, and run the epilogues straight out of TMEM
+//               (a full row lives in one thread, so both LayerNorms need no cross-thread traffic).
+// Precision: every 256x256 product is evaluated as  a_hi*b_hi + a_lo*b_hi + a_hi*b_lo  with
+// a = a_hi + a_lo, b = b_hi + b_lo in bf16 and fp32 accumulation in TMEM: ~2^-17 relative error
+// per product, which keeps the 1e-4 fp32 contract (single-pass TF32/BF16 does not: SURVEY D9).
+// The two 128x256 fp32 accumulators (GEMM1, GEMM2) take the full 512 TMEM columns.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <string>
+
+#include "common.cuh"
+#include "edge_layer_fp32.cuh"   // AGG_*
+
+namespace dfb {
+
+constexpr int TC_TILE = 128;
+constexpr int TC_THREADS = 192;
+constexpr int TC_KCH = 64;                         // K elements per chunk = one 128-byte swizzle row
+constexpr int TC_A_BYTES = TC_TILE * 128;          // 16 KB  (hi or lo)
+constexpr int TC_B_BYTES = 256 * 128;              // 32 KB  (hi or lo)
+constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;   // 96 KB
+constexpr int TC_NSTAGE = 2;
+constexpr int TC_OFF_PRM = TC_NSTAGE * TC_STAGE_BYTES;            // 6 x 256 floats
+constexpr int TC_OFF_PATCH = TC_OFF_PRM + 6 * H * 4;              // 4 warps x 32 x 33 floats
+constexpr int TC_OFF_ROW = TC_OFF_PATCH + 4 * 32 * 33 * 4;
+constexpr int TC_OFF_COL = TC_OFF_ROW + TC_TILE * 4;
+constexpr int TC_OFF_SRC = TC_OFF_COL + TC_TILE * 4;
+constexpr int TC_OFF_BAR = TC_OFF_SRC + TC_TILE * 8;
+constexpr int TC_SMEM_BYTES = TC_OFF_BAR + 128;
+constexpr int TC_SMEM_ALLOC = TC_SMEM_BYTES + 1024;               // slack for 1024-byte alignment
+// UMMA instruction descriptor: D=F32, A=B=BF16, both K-major, N=256, M=128 (cute::UMMA::InstrDescriptor)
+constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+
+struct TcParams {
+  float* e;
+  const float* uvab;
+  float* partials;
+  GraphDev g;
+  LayerParams lp;
+  const float* tvec;      // [256] time vector added on edges (TSP) or nullptr (MIS)
+  const float* xt_lut;    // layer 0 categorical: edge values in {0,1} (caller order) or nullptr
+  const float* lut;       // [2][256]
+  const float* zero_row;  // [256] zeros
+  float* debug_acc;       // tests: dump GEMM1 accumulator [E][256] and stop
+  int* error_flag;
+  int write_e, e_zero, agg_mode;
+  int w_row_base;         // row of this layer's C_hi block in the bf16 weight arena tensor map
+  int n_tiles;
+};
+
+// ----------------------------------------------------------------------------------------------
+// PTX wrappers
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// Bounded wait: a protocol bug must surface as a launch failure, not as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* error_flag, int code) {
+  uint32_t addr = smem_u32(bar), ok = 0;
+  long long t0 = 0;
+  for (uint32_t spin = 0;; ++spin) {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if ((spin & 1023u) == 1023u) {
+      long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000LL) {   // ~2 s at 2 GHz
+        if (error_flag) atomicExch(error_flag, code);
+        __threadfence_system();
+        __trap();
+      }
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
+      " tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(TC_IDESC), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// K-major, 128-byte swizzle, 8-row atoms 1024 bytes apart (cute::UMMA::SmemDescriptor, version 1)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  const uint64_t hi = 64ull | (1ull << 14) | (2ull << 29);
+  return (hi << 32) | (1ull << 16) | (uint64_t)((smem_addr >> 4) & 0x3fffu);
+}
+
+#define TC_R32(v) \
+  "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),       \
+  "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),            \
+  "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),           \
+  "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+#define TC_W32(v) \
+  "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),     \
+  "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),       \
+  "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),       \
+  "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+
+// 32 lanes x 32 columns: thread <lane> of the warp gets 32 consecutive fp32 columns of its TMEM lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : TC_R32(v)
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%32], "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31};"
+      ::TC_W32(v), "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// fp32 x4 -> bf16 hi x4, bf16 lo x4 (lo = rn(x - hi))
+__device__ __forceinline__ void split4(float4 x, uint2& hi, uint2& lo) {
+  __nv_bfloat162 h01 = __floats2bfloat162_rn(x.x, x.y), h23 = __floats2bfloat162_rn(x.z, x.w);
+  float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+  __nv_bfloat162 l01 = __floats2bfloat162_rn(x.x - f01.x, x.y - f01.y);
+  __nv_bfloat162 l23 = __floats2bfloat162_rn(x.z - f23.x, x.w - f23.y);
+  hi.x = *reinterpret_cast<uint32_t*>(&h01);
+  hi.y = *reinterpret_cast<uint32_t*>(&h23);
+  lo.x = *reinterpret_cast<uint32_t*>(&l01);
+  lo.y = *reinterpret_cast<uint32_t*>(&l23);
+}
+// byte offset of (row r, 16-byte unit j in [0,8)) inside a [rows][64 bf16] K-major 128B-swizzled tile
+__device__ __forceinline__ uint32_t sw128_off(int r, int j) {
+  return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4));
+}
+
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_edge_layer_tc(const __grid_constant__ CUtensorMap wmap, const TcParams P) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  float* prm = reinterpret_cast<float*>(smem + TC_OFF_PRM);      // ln_e_g, ln_e_b, tau, ln_o_g, ln_o_b, b_O
+  float* patch_all = reinterpret_cast<float*>(smem + TC_OFF_PATCH);
+  int* s_row = reinterpret_cast<int*>(smem + TC_OFF_ROW);
+  int* s_col = reinterpret_cast<int*>(smem + TC_OFF_COL);
+  const float** s_src = reinterpret_cast<const float**>(smem + TC_OFF_SRC);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_OFF_BAR);
+  uint64_t* full_a = bars;        // [2] workers -> MMA   (128 arrivals)
+  uint64_t* full_b = bars + 2;    // [2] TMA     -> MMA   (expect_tx)
+  uint64_t* empty = bars + 4;     // [2] MMA commit -> producer + workers
+  uint64_t* acc_rdy = bars + 6;   // [2] MMA commit -> workers (GEMM1, GEMM2 accumulators complete)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int uses_per_tile = P.write_e ? 8 : 4;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&full_a[0], 128); mbar_init(&full_a[1], 128);
+    mbar_init(&full_b[0], 1);   mbar_init(&full_b[1], 1);
+    mbar_init(&empty[0], 1);    mbar_init(&empty[1], 1);
+    mbar_init(&acc_rdy[0], 1);  mbar_init(&acc_rdy[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_proxy_async();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < H; i += TC_THREADS) {
+    prm[i] = P.lp.ln_e_g[i];
+    prm[H + i] = P.lp.ln_e_b[i];
+    prm[2 * H + i] = P.tvec ? P.tvec[i] : 0.0f;
+    prm[3 * H + i] = P.lp.ln_o_g[i];
+    prm[4 * H + i] = P.lp.ln_o_b[i];
+    prm[5 * H + i] = P.lp.b_O[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t smem_base = smem_u32(smem);
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      uint32_t u = 0;
+      for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+        for (int i = 0; i < uses_per_tile; ++i, ++u) {
+          const int s = u & 1, k = u >> 1, kc = i & 3;
+          mbar_wait(&empty[s], (k & 1) ^ 1, P.error_flag, 1);
+          mbar_arrive_expect_tx(&full_b[s], 2 * TC_B_BYTES);
+          const uint32_t dst = smem_base + s * TC_STAGE_BYTES + 2 * TC_A_BYTES;
+          const int rb = P.w_row_base + (i < 4 ? 0 : 512);   // C_hi,C_lo | O_hi,O_lo blocks of 256 rows
+          tma_load_2d(dst, &wmap, &full_b[s], kc * TC_KCH, rb);
+          tma_load_2d(dst + TC_B_BYTES, &wmap, &full_b[s], kc * TC_KCH, rb + 256);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =======================================
+    if (lane == 0) {
+      uint32_t u = 0;
+      for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+        for (int i = 0; i < uses_per_tile; ++i, ++u) {
+          const int s = u & 1, k = u >> 1, kc = i & 3;
+          mbar_wait(&full_b[s], k & 1, P.error_flag, 2);
+          mbar_wait(&full_a[s], k & 1, P.error_flag, 3);
+          tc_fence_after();
+          const uint32_t a_hi = smem_base + s * TC_STAGE_BYTES, a_lo = a_hi + TC_A_BYTES;
+          const uint32_t b_hi = a_hi + 2 * TC_A_BYTES, b_lo = b_hi + TC_B_BYTES;
+          const uint32_t d = tmem_base + (i < 4 ? 0u : 256u);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t dah = umma_desc_sw128(a_hi + ks * 32), dal = umma_desc_sw128(a_lo + ks * 32);
+            const uint64_t dbh = umma_desc_sw128(b_hi + ks * 32), dbl = umma_desc_sw128(b_lo + ks * 32);
+            umma_bf16(d, dah, dbh, (kc | ks) ? 1u : 0u);
+            umma_bf16(d, dal, dbh, 1u);
+            umma_bf16(d, dah, dbl, 1u);
+          }
+          umma_commit(&empty[s]);                       // frees the stage when these MMAs have read it
+          if (kc == 3) umma_commit(&acc_rdy[i < 4 ? 0 : 1]);
+        }
+      }
+    }
+  } else {
+    // ===================================== row workers ======================================
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;            // tile row == TMEM lane
+    float* patch = patch_all + q * 32 * 33;
+    const uint32_t t_acc1 = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t t_acc2 = t_acc1 + 256u;
+    uint32_t u = 0, tile_it = 0;
+    for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++tile_it) {
+      const int s_edge = tile * TC_TILE + r;
+      const bool valid = s_edge < P.g.E;
+      int my_row = -1, my_col = 0;
+      const float* src = P.zero_row;
+      if (valid) {
+        my_row = P.g.row[s_edge];
+        my_col = P.g.col[s_edge];
+        if (P.e_zero) src = P.zero_row;
+        else if (P.xt_lut) src = P.lut + ((P.xt_lut[P.g.perm ? P.g.perm[s_edge] : s_edge] != 0.0f) ? H : 0);
+        else src = P.e + (size_t)s_edge * H;
+      }
+      s_row[r] = my_row;
+      s_col[r] = my_col;
+      s_src[r] = src;
+      uint32_t seg_mask;
+      {
+        int next_row = __shfl_down_sync(0xffffffffu, my_row, 1);
+        bool seg_end = valid && (lane == 31 || next_row != my_row);
+        seg_mask = __ballot_sync(0xffffffffu, seg_end);
+      }
+      __syncwarp();   // conversion below only reads this warp's own 32 rows of s_src
+
+      // ---------------- GEMM1 A operand: fp32 edge rows -> bf16 hi/lo swizzled chunks ----------------
+      for (int kc = 0; kc < 4; ++kc, ++u) {
+        const int s = u & 1, k = u >> 1;
+        float4 x[16];
+#pragma unroll
+        for (int it = 0; it < 16; ++it) {
+          const int rr = q * 32 + it * 2 + (lane >> 4);
+          x[it] = __ldg(reinterpret_cast<const float4*>(s_src[rr] + kc * TC_KCH) + (lane & 15));
+        }
+        mbar_wait(&empty[s], (k & 1) ^ 1, P.error_flag, 4);
+        unsigned char* a_hi = smem + s * TC_STAGE_BYTES;
+        unsigned char* a_lo = a_hi + TC_A_BYTES;
+#pragma unroll
+        for (int it = 0; it < 16; ++it) {
+          const int rr = q * 32 + it * 2 + (lane >> 4);
+          const int k4 = lane & 15;
+          uint2 hi, lo;
+          split4(x[it], hi, lo);
+          const uint32_t off = sw128_off(rr, k4 >> 1) + (k4 & 1) * 8;
+          *reinterpret_cast<uint2*>(a_hi + off) = hi;
+          *reinterpret_cast<uint2*>(a_lo + off) = lo;
+        }
+        fence_proxy_async();
+        tc_fence_before();   // orders this thread's earlier TMEM reads (previous tile) before the MMA overwrites
+        mbar_arrive(&full_a[s]);
+      }
+
+      // ---------------- E1: e_hat, gate, messages, row statistics ----------------
+      mbar_wait(&acc_rdy[0], tile_it & 1, P.error_flag, 5);
+      tc_fence_after();
+      if (P.debug_acc) {
+#pragma unroll 1
+        for (int c0 = 0; c0 < H; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(t_acc1 + c0, v);
+          tmem_wait_ld();
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) P.debug_acc[(size_t)s_edge * H + c0 + j] = __uint_as_float(v[j]);
+          }
+        }
+        tc_fence_before();
+        continue;
+      }
+      const float* uv_col = P.uvab + (size_t)my_col * 4 * H;
+      const float* uv_row = P.uvab + (size_t)(valid ? my_row : 0) * 4 * H;
+      const int grp = tile * 4 + q;
+      const int first_node = (grp < P.g.n_groups) ? P.g.grp_first[grp] : 0;
+      const size_t pair_base = (grp < P.g.n_groups) ? (size_t)P.g.grp_pair[grp] : 0;
+      float K1 = 0.f, S1 = 0.f, Q1 = 0.f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < H; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(t_acc1 + c0, v);
+        tmem_wait_ld();
+        const float4* pa = reinterpret_cast<const float4*>(uv_col + 2 * H + c0);
+        const float4* pb = reinterpret_cast<const float4*>(uv_row + 3 * H + c0);
+        const float4* pv = reinterpret_cast<const float4*>(uv_col + H + c0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 a = __ldg(pa + j), b = __ldg(pb + j), vv = __ldg(pv + j);
+          float xs[4] = {__uint_as_float(v[4 * j]) + a.x + b.x, __uint_as_float(v[4 * j + 1]) + a.y + b.y,
+                         __uint_as_float(v[4 * j + 2]) + a.z + b.z, __uint_as_float(v[4 * j + 3]) + a.w + b.w};
+          const float vs[4] = {vv.x, vv.y, vv.z, vv.w};
+          if (c0 == 0 && j == 0) K1 = xs[0];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float d = xs[i] - K1;
+            S1 += d;
+            Q1 = fmaf(d, d, Q1);
+            float m = sigmoidf_fast(xs[i]) * vs[i];
+            if (!valid) m = (P.agg_mode == AGG_MAX) ? -INFINITY : 0.0f;
+            patch[lane * 33 + 4 * j + i] = m;
+            v[4 * j + i] = __float_as_uint(xs[i]);
+          }
+        }
+        if (P.write_e) tmem_st32(t_acc1 + c0, v);
+        __syncwarp();
+        // transposed pass: lane == column, walk the warp's 32 rows, flush at segment ends
+        {
+          float run = (P.agg_mode == AGG_MAX) ? -INFINITY : 0.0f;
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr) {
+            const float m = patch[rr * 33 + lane];
+            run = (P.agg_mode == AGG_MAX) ? fmaxf(run, m) : run + m;
+            if ((seg_mask >> rr) & 1u) {
+              const int node = s_row[q * 32 + rr];
+              P.partials[(pair_base + (size_t)(node - first_node)) * H + c0 + lane] = run;
+              run = (P.agg_mode == AGG_MAX) ? -INFINITY : 0.0f;
+            }
+          }
+        }
+        __syncwarp();
+      }
+      if (!P.write_e) {   // MIS last layer: edge stream is dead (gnn_encoder.py:412)
+        tmem_wait_ld();
+        tc_fence_before();
+        continue;
+      }
+      tmem_wait_st();
+      const float mean1 = K1 + S1 * (1.0f / H);
+      const float var1 = fmaxf(Q1 * (1.0f / H) - (S1 * (1.0f / H)) * (S1 * (1.0f / H)), 0.0f);
+      const float rstd1 = rsqrtf(var1 + LN_EPS);
+
+      // ---------------- E2: e_til = relu(LN_e(e_hat)) + tau, statistics for LN_O ----------------
+      float K2 = 0.f, S2 = 0.f, Q2 = 0.f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < H; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(t_acc1 + c0, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int c = c0 + j;
+          float y = fmaxf(fmaf((__uint_as_float(v[j]) - mean1) * rstd1, prm[c], prm[H + c]), 0.0f) + prm[2 * H + c];
+          if (c == 0) K2 = y;
+          const float d = y - K2;
+          S2 += d;
+          Q2 = fmaf(d, d, Q2);
+          v[j] = __float_as_uint(y);
+        }
+        tmem_st32(t_acc1 + c0, v);
+      }
+      tmem_wait_st();
+      const float mean2 = K2 + S2 * (1.0f / H);
+      const float var2 = fmaxf(Q2 * (1.0f / H) - (S2 * (1.0f / H)) * (S2 * (1.0f / H)), 0.0f);
+      const float rstd2 = rsqrtf(var2 + LN_EPS);
+
+      // ---------------- E3: s = silu(LN_O(e_til)) -> GEMM2 A operand chunks ----------------
+#pragma unroll 1
+      for (int kc = 0; kc < 4; ++kc, ++u) {
+        const int s = u & 1, k = u >> 1;
+        unsigned char* a_hi = smem + s * TC_STAGE_BYTES;
+        unsigned char* a_lo = a_hi + TC_A_BYTES;
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          const int c0 = kc * TC_KCH + half * 32;
+          uint32_t v[32];
+          tmem_ld32(t_acc1 + c0, v);
+          tmem_wait_ld();
+          if (half == 0) mbar_wait(&empty[s], (k & 1) ^ 1, P.error_flag, 6);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {   // 4 x 16-byte units of 8 bf16
+            float z[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int c = c0 + 8 * j + i;
+              const float t = fmaf((__uint_as_float(v[8 * j + i]) - mean2) * rstd2, prm[3 * H + c], prm[4 * H + c]);
+              z[i] = t * sigmoidf_fast(t);
+            }
+            uint2 h0, l0, h1, l1;
+            split4(make_float4(z[0], z[1], z[2], z[3]), h0, l0);
+            split4(make_float4(z[4], z[5], z[6], z[7]), h1, l1);
+            const uint32_t off = sw128_off(r, half * 4 + j);
+            *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+            *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+          }
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive(&full_a[s]);
+      }
+
+      // ---------------- E4: e = e_in + O(s) + b_O ----------------
+      mbar_wait(&acc_rdy[1], tile_it & 1, P.error_flag, 7);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < H; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(t_acc2 + c0, v);
+        tmem_wait_ld();
+        if (valid) {
+          const float4* pin = reinterpret_cast<const float4*>(src + c0);
+          float4* pout = reinterpret_cast<float4*>(P.e + (size_t)s_edge * H + c0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 ein = __ldg(pin + j);
+            float4 o;
+            o.x = ein.x + __uint_as_float(v[4 * j]) + prm[5 * H + c0 + 4 * j];
+            o.y = ein.y + __uint_as_float(v[4 * j + 1]) + prm[5 * H + c0 + 4 * j + 1];
+            o.z = ein.z + __uint_as_float(v[4 * j + 2]) + prm[5 * H + c0 + 4 * j + 2];
+            o.w = ein.w + __uint_as_float(v[4 * j + 3]) + prm[5 * H + c0 + 4 * j + 3];
+            pout[j] = o;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+    }
+  }
+
+  // teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------------------
+struct TcState {
+  std::string err;
+  int num_sms = 0;
+  CUtensorMap wmap;
+  bool bound = false;
+  int last_launches = 0;
+  float* zero_row = nullptr;
+  int* error_flag = nullptr;
+  float* debug_acc = nullptr;   // set by the debug entry point for one launch
+};
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline int tc_init(TcState* st, int num_sms) {
+  st->num_sms = num_sms;
+  cudaError_t e = cudaFuncSetAttribute(k_edge_layer_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_ALLOC);
+  if (e != cudaSuccess) {
+    st->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e);
+    return -2;
+  }
+  if ((e = cudaMalloc(&st->zero_row, H * sizeof(float))) != cudaSuccess ||
+      (e = cudaMemset(st->zero_row, 0, H * sizeof(float))) != cudaSuccess ||
+      (e = cudaMalloc(&st->error_flag, sizeof(int))) != cudaSuccess ||
+      (e = cudaMemset(st->error_flag, 0, sizeof(int))) != cudaSuccess) {
+    st->err = std::string("tc_init alloc: ") + cudaGetErrorString(e);
+    return -2;
+  }
+  return 0;
+}
+
+inline void tc_destroy(TcState* st) {
+  if (st->zero_row) cudaFree(st->zero_row);
+  if (st->error_flag) cudaFree(st->error_flag);
+  st->zero_row = nullptr;
+  st->error_flag = nullptr;
+}
+
+// One tensor map over the whole bf16 weight arena: [L*4*256 rows][256 K], rows of layer l are
+// C_hi | C_lo | O_hi | O_lo (256 rows each).  Box = 64 K x 256 rows, 128-byte swizzle.
+inline int tc_bind_weights(TcState* st, const LayerParams* layers, int L) {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || !fn || qres != cudaDriverEntryPointSuccess) {
+    st->err = "cuTensorMapEncodeTiled entry point not available";
+    cudaGetLastError();
+    return -2;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)H, (cuuint64_t)L * 4 * H};
+  cuuint64_t gstride[1] = {(cuuint64_t)H * sizeof(uint16_t)};
+  cuuint32_t box[2] = {(cuuint32_t)TC_KCH, 256u};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = ((PFN_encodeTiled)fn)(&st->wmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)layers[0].C_hi, gdim,
+                                     gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    st->err = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r);
+    return -2;
+  }
+  st->bound = true;
+  return 0;
+}
+
+inline int tc_launch_edge_layer(TcState* st, int l, float* e, const float* uvab, float* partials, GraphDev g,
+                                LayerParams lp, const float* tvec_edge, int write_e, int e_zero,
+                                const float* xt_lut, const float* lut, int agg_mode, cudaStream_t stream) {
+  st->last_launches = 0;
+  if (!st->bound) {
+    st->err = "weights not bound";
+    return -1;
+  }
+  TcParams P;
+  P.e = e; P.uvab = uvab; P.partials = partials; P.g = g; P.lp = lp; P.tvec = tvec_edge;
+  P.xt_lut = xt_lut; P.lut = lut; P.zero_row = st->zero_row; P.debug_acc = st->debug_acc;
+  P.error_flag = st->error_flag;
+  P.write_e = st->debug_acc ? 0 : write_e;
+  P.e_zero = e_zero; P.agg_mode = agg_mode;
+  P.w_row_base = l * 4 * H;
+  P.n_tiles = (g.E + TC_TILE - 1) / TC_TILE;
+  int grid = P.n_tiles < st->num_sms ? P.n_tiles : st->num_sms;
+  k_edge_layer_tc<<<grid, TC_THREADS, TC_SMEM_ALLOC, stream>>>(st->wmap, P);
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) {
+    st->err = std::string("launch: ") + cudaGetErrorString(err);
+    return -2;
+  }
+  st->last_launches = 1;
+  return 0;
+}
+
+}  // namespace dfb
