@@ -123,10 +123,10 @@ def cpu_oracle_graphs_per_s(denoise_steps_sample, threads=None):
   xt = torch.from_numpy(xt0)
   ei_t = torch.from_numpy(ei)
   with torch.no_grad():
-    orc.encoder_forward_sparse_tsp(w, pts, xt, torch.tensor([1000.0]), ei_t)   # warm-up forward
+    orc.encoder_forward_sparse_tsp(w, pts, xt, torch.tensor([1000.0]), ei_t, gather_then_gemm=False)   # warm-up
     t0 = time.perf_counter()
     for (t1, t2) in sched[:denoise_steps_sample]:
-      out = orc.encoder_forward_sparse_tsp(w, pts, xt, torch.tensor([float(t1)]), ei_t)
+      out = orc.encoder_forward_sparse_tsp(w, pts, xt, torch.tensor([float(t1)]), ei_t, gather_then_gemm=False)
       _, xt = orc.categorical_posterior(Qbar, t1, t2, out.softmax(-1), xt)
     dt = time.perf_counter() - t0
   per_graph = dt * DENOISE_STEPS / denoise_steps_sample
