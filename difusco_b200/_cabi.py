@@ -19,6 +19,7 @@ SYMBOLS = [
     "dfb_set_edge_impl", "dfb_load_weights", "dfb_prepare_graph", "dfb_set_points",
     "dfb_encoder_forward", "dfb_denoise_step", "dfb_denoise", "dfb_denoise_host",
     "dfb_launch_count", "dfb_profile_begin", "dfb_profile_end", "dfb_debug_edge_gemm",
+    "dfb_debug_phase_cycles",
 ]
 
 _lib = None
@@ -56,6 +57,7 @@ def lib():
   L.dfb_profile_begin.argtypes = [vp]
   L.dfb_profile_end.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64)]
   L.dfb_debug_edge_gemm.argtypes = [vp, i32, vp, vp, vp]
+  L.dfb_debug_phase_cycles.argtypes = [vp, C.POINTER(C.c_uint64)]
   for name in SYMBOLS:
     fn = getattr(L, name)
     if fn.restype is C.c_int and name not in ("dfb_abi_version",):
@@ -177,6 +179,11 @@ class Context(object):
     ms, n = C.c_double(0), C.c_int64(0)
     self._ck(lib().dfb_profile_end(self._h, C.byref(ms), C.byref(n)))
     return ms.value, n.value
+
+  def debug_phase_cycles(self):
+    out = (C.c_uint64 * 8)()
+    self._ck(lib().dfb_debug_phase_cycles(self._h, out))
+    return [int(x) for x in out]
 
   def debug_edge_gemm(self, layer, e_in_ptr, acc_out_ptr, stream=0):
     self._ck(lib().dfb_debug_edge_gemm(self._h, layer, e_in_ptr, acc_out_ptr, stream))

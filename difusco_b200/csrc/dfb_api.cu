@@ -634,7 +634,7 @@ static int run_forward(dfb_ctx* ctx, const float* xt, const float* tvec, bool bi
     if (r) return r;
     if (ctx->node_only || l < L - 1) {   // TSP never reads h after the last layer (gnn_encoder.py:400)
       k_node_update<<<(V + 7) / 8, 256, 0, st>>>(h, uv, (const float*)ctx->partials.p, g, ctx->layers[l].ln_h_g,
-                                                 ctx->layers[l].ln_h_b, ctx->node_only ? tv : nullptr);
+                                                 ctx->layers[l].ln_h_b, ctx->node_only ? tv : nullptr, ctx->agg_mode);
       CKL(ctx);
     }
   }
@@ -802,5 +802,16 @@ extern "C" int dfb_debug_edge_gemm(dfb_ctx* ctx, int layer, const float* e_in, f
   ctx->tc.debug_acc = nullptr;
   if (r) FAIL(ctx, DFB_E_CUDA, "tcgen05 edge layer: %s", ctx->tc.err.c_str());
   ctx->launches += 1;
+  return DFB_OK;
+}
+
+// Test/tuning hook: read and reset the per-phase cycle counters of the tcgen05 edge kernel
+// (filled only when DFB_TC_PROBE has bit 7 set).  out[8] host.
+extern "C" int dfb_debug_phase_cycles(dfb_ctx* ctx, unsigned long long* out) {
+  if (!ctx || !out) return DFB_E_INVALID;
+  CK(ctx, cudaSetDevice(ctx->device));
+  CK(ctx, cudaDeviceSynchronize());
+  CK(ctx, cudaMemcpy(out, ctx->tc.phase_cycles, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  CK(ctx, cudaMemset(ctx->tc.phase_cycles, 0, 8 * sizeof(unsigned long long)));
   return DFB_OK;
 }

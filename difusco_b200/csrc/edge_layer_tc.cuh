@@ -21,6 +21,8 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <stdlib.h>
+
 #include <string>
 
 #include "common.cuh"
@@ -29,20 +31,12 @@
 namespace dfb {
 
 constexpr int TC_TILE = 128;
-constexpr int TC_THREADS = 192;
 constexpr int TC_KCH = 64;                         // K elements per chunk = one 128-byte swizzle row
 constexpr int TC_A_BYTES = TC_TILE * 128;          // 16 KB  (hi or lo)
 constexpr int TC_B_BYTES = 256 * 128;              // 32 KB  (hi or lo)
 constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;   // 96 KB
 constexpr int TC_NSTAGE = 2;
 constexpr int TC_OFF_PRM = TC_NSTAGE * TC_STAGE_BYTES;            // 6 x 256 floats
-constexpr int TC_OFF_PATCH = TC_OFF_PRM + 6 * H * 4;              // 4 warps x 32 x 33 floats
-constexpr int TC_OFF_ROW = TC_OFF_PATCH + 4 * 32 * 33 * 4;
-constexpr int TC_OFF_COL = TC_OFF_ROW + TC_TILE * 4;
-constexpr int TC_OFF_SRC = TC_OFF_COL + TC_TILE * 4;
-constexpr int TC_OFF_BAR = TC_OFF_SRC + TC_TILE * 8;
-constexpr int TC_SMEM_BYTES = TC_OFF_BAR + 128;
-constexpr int TC_SMEM_ALLOC = TC_SMEM_BYTES + 1024;               // slack for 1024-byte alignment
 // UMMA instruction descriptor: D=F32, A=B=BF16, both K-major, N=256, M=128 (cute::UMMA::InstrDescriptor)
 constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
 
@@ -61,6 +55,9 @@ struct TcParams {
   int write_e, e_zero, agg_mode;
   int w_row_base;         // row of this layer's C_hi block in the bf16 weight arena tensor map
   int n_tiles;
+  unsigned long long* phase_cycles;   // [8] probe bit 7: per-phase cycle sums of worker thread 0, all CTAs
+  int probe;   // timing experiments only (DFB_TC_PROBE env): bit0 no gathers, bit1 no segment reduce, bit2 no E2,
+               // bit3 no E3 math, bit4 no E4 load/store, bit5 no conversion loads, bit6 no sigmoid
 };
 
 // ----------------------------------------------------------------------------------------------
@@ -77,25 +74,23 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-// Bounded wait: a protocol bug must surface as a launch failure, not as a hung GPU.
+// Bounded wait: a protocol bug must surface as a launch failure, not as a hung GPU.  try_wait suspends
+// the thread in hardware (up to the hint, in ns) instead of burning issue slots.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* error_flag, int code) {
-  uint32_t addr = smem_u32(bar), ok = 0;
-  long long t0 = 0;
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok = 0;
+#pragma unroll 1
   for (uint32_t spin = 0;; ++spin) {
     asm volatile(
-        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}"
         : "=r"(ok)
-        : "r"(addr), "r"(parity)
+        : "r"(addr), "r"(parity), "r"(20000u)
         : "memory");
     if (ok) return;
-    if ((spin & 1023u) == 1023u) {
-      long long now = clock64();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 4000000000LL) {   // ~2 s at 2 GHz
-        if (error_flag) atomicExch(error_flag, code);
-        __threadfence_system();
-        __trap();
-      }
+    if (spin > 400000u) {   // >> any legitimate wait (each failed try_wait already slept up to 20 us)
+      if (error_flag) atomicExch(error_flag, code);
+      __threadfence_system();
+      __trap();
     }
   }
 }
@@ -158,6 +153,13 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// sigmoid with one MUFU.EX2 and one MUFU.RCP (ex2.approx: 2 ulp, rcp.approx: 1 ulp -> ~3e-7 relative)
+__device__ __forceinline__ float sigmoid_mufu(float x) {
+  float t, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(-1.4426950408889634f * x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + t));
+  return r;
+}
 // fp32 x4 -> bf16 hi x4, bf16 lo x4 (lo = rn(x - hi))
 __device__ __forceinline__ void split4(float4 x, uint2& hi, uint2& lo) {
   __nv_bfloat162 h01 = __floats2bfloat162_rn(x.x, x.y), h23 = __floats2bfloat162_rn(x.z, x.w);
@@ -175,30 +177,55 @@ __device__ __forceinline__ uint32_t sw128_off(int r, int j) {
 }
 
 // ----------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// WPQ = worker warps per TMEM lane quarter.  The 256 channels of a row are split into WPQ contiguous
+// slices, one per warp of the quarter (warps with equal warp_id % 4 may touch the same TMEM lanes);
+// LayerNorm partial statistics of the slices are combined through shared memory.
+template <int WPQ>
+struct TcCfg {
+  static constexpr int NWORK = 128 * WPQ;                 // worker threads
+  static constexpr int THREADS = 64 + NWORK;
+  static constexpr int CPP = H / WPQ;                     // columns per part
+  static constexpr int PATCH_COLS = (WPQ == 4) ? 4 : 32 / WPQ;
+  static constexpr int OFF_PATCH = TC_OFF_PRM + 6 * H * 4;
+  static constexpr int OFF_STAT1 = OFF_PATCH + 4 * WPQ * PATCH_COLS * 36 * 4;
+  static constexpr int OFF_STAT2 = OFF_STAT1 + WPQ * TC_TILE * 16;
+  static constexpr int OFF_ROW = OFF_STAT2 + WPQ * TC_TILE * 8;
+  static constexpr int OFF_SRC = OFF_ROW + TC_TILE * 4;
+  static constexpr int OFF_BAR = OFF_SRC + TC_TILE * 8;
+  static constexpr int SMEM_BYTES = OFF_BAR + 128;
+  static constexpr int SMEM_ALLOC = SMEM_BYTES + 1024;    // slack for 1024-byte alignment
+  static_assert(SMEM_ALLOC <= 232448, "shared memory budget");
+};
+
+template <int WPQ>
+__global__ void __launch_bounds__(TcCfg<WPQ>::THREADS, 1)
 k_edge_layer_tc(const __grid_constant__ CUtensorMap wmap, const TcParams P) {
+  using Cfg = TcCfg<WPQ>;
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays in .shared
   float* prm = reinterpret_cast<float*>(smem + TC_OFF_PRM);      // ln_e_g, ln_e_b, tau, ln_o_g, ln_o_b, b_O
-  float* patch_all = reinterpret_cast<float*>(smem + TC_OFF_PATCH);
-  int* s_row = reinterpret_cast<int*>(smem + TC_OFF_ROW);
-  int* s_col = reinterpret_cast<int*>(smem + TC_OFF_COL);
-  const float** s_src = reinterpret_cast<const float**>(smem + TC_OFF_SRC);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_OFF_BAR);
-  uint64_t* full_a = bars;        // [2] workers -> MMA   (128 arrivals)
-  uint64_t* full_b = bars + 2;    // [2] TMA     -> MMA   (expect_tx)
-  uint64_t* empty = bars + 4;     // [2] MMA commit -> producer + workers
-  uint64_t* acc_rdy = bars + 6;   // [2] MMA commit -> workers (GEMM1, GEMM2 accumulators complete)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  float* patch_all = reinterpret_cast<float*>(smem + Cfg::OFF_PATCH);
+  float4* stat1 = reinterpret_cast<float4*>(smem + Cfg::OFF_STAT1);   // [WPQ][128] (K, S, Q, -)
+  float2* stat2 = reinterpret_cast<float2*>(smem + Cfg::OFF_STAT2);   // [WPQ][128] (S, Q)
+  int* s_row = reinterpret_cast<int*>(smem + Cfg::OFF_ROW);
+  const float** s_src = reinterpret_cast<const float**>(smem + Cfg::OFF_SRC);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint64_t* full_a1 = bars;       // [2] all workers -> MMA (GEMM1 A chunks, NWORK arrivals)
+  uint64_t* full_a2 = bars + 2;   // [2] owning part  -> MMA (GEMM2 A chunks, 128 arrivals)
+  uint64_t* full_b = bars + 4;    // [2] TMA -> MMA (expect_tx)
+  uint64_t* empty = bars + 6;     // [2] MMA commit -> producer + workers
+  uint64_t* acc_rdy = bars + 8;   // [2] MMA commit -> workers (GEMM1 / GEMM2 accumulator complete)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int uses_per_tile = P.write_e ? 8 : 4;
 
   if (threadIdx.x == 0) {
-    mbar_init(&full_a[0], 128); mbar_init(&full_a[1], 128);
-    mbar_init(&full_b[0], 1);   mbar_init(&full_b[1], 1);
-    mbar_init(&empty[0], 1);    mbar_init(&empty[1], 1);
-    mbar_init(&acc_rdy[0], 1);  mbar_init(&acc_rdy[1], 1);
+    mbar_init(&full_a1[0], Cfg::NWORK); mbar_init(&full_a1[1], Cfg::NWORK);
+    mbar_init(&full_a2[0], 128);        mbar_init(&full_a2[1], 128);
+    mbar_init(&full_b[0], 1);           mbar_init(&full_b[1], 1);
+    mbar_init(&empty[0], 1);            mbar_init(&empty[1], 1);
+    mbar_init(&acc_rdy[0], 1);          mbar_init(&acc_rdy[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_proxy_async();
   }
@@ -207,7 +234,7 @@ k_edge_layer_tc(const __grid_constant__ CUtensorMap wmap, const TcParams P) {
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < H; i += TC_THREADS) {
+  for (int i = threadIdx.x; i < H; i += Cfg::THREADS) {
     prm[i] = P.lp.ln_e_g[i];
     prm[H + i] = P.lp.ln_e_b[i];
     prm[2 * H + i] = P.tvec ? P.tvec[i] : 0.0f;
@@ -226,6 +253,11 @@ k_edge_layer_tc(const __grid_constant__ CUtensorMap wmap, const TcParams P) {
     if (lane == 0) {
       uint32_t u = 0;
       for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+        if (!P.e_zero && !P.xt_lut && tile + (int)gridDim.x < P.n_tiles && !(P.probe & 256)) {
+          // the next tile's 128 edge rows are one contiguous 128 KB block: pull it into L2 now
+          const float* nxt = P.e + (size_t)(tile + gridDim.x) * TC_TILE * H;
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nxt), "r"(TC_TILE * H * 4) : "memory");
+        }
         for (int i = 0; i < uses_per_tile; ++i, ++u) {
           const int s = u & 1, k = u >> 1, kc = i & 3;
           mbar_wait(&empty[s], (k & 1) ^ 1, P.error_flag, 1);
@@ -245,7 +277,8 @@ k_edge_layer_tc(const __grid_constant__ CUtensorMap wmap, const TcParams P) {
         for (int i = 0; i < uses_per_tile; ++i, ++u) {
           const int s = u & 1, k = u >> 1, kc = i & 3;
           mbar_wait(&full_b[s], k & 1, P.error_flag, 2);
-          mbar_wait(&full_a[s], k & 1, P.error_flag, 3);
+          // each A barrier of a stage completes twice per tile (chunks kc, kc+2): parity (kc>>1)&1
+          mbar_wait(i < 4 ? &full_a1[s] : &full_a2[s], (kc >> 1) & 1, P.error_flag, 3);
           tc_fence_after();
           const uint32_t a_hi = smem_base + s * TC_STAGE_BYTES, a_lo = a_hi + TC_A_BYTES;
           const uint32_t b_hi = a_hi + 2 * TC_A_BYTES, b_lo = b_hi + TC_B_BYTES;
@@ -265,13 +298,21 @@ k_edge_layer_tc(const __grid_constant__ CUtensorMap wmap, const TcParams P) {
     }
   } else {
     // ===================================== row workers ======================================
-    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access (hardware rule)
+    const int part = (warp - 2) >> 2;       // which column slice of the row
     const int r = q * 32 + lane;            // tile row == TMEM lane
-    float* patch = patch_all + q * 32 * 33;
+    const int wt = (warp - 2) * 32 + lane;  // worker thread index, 0 .. NWORK-1
+    const int cbase = part * Cfg::CPP;
+    float* patch = patch_all + (warp - 2) * Cfg::PATCH_COLS * 36;
     const uint32_t t_acc1 = tmem_base + ((uint32_t)(q * 32) << 16);
     const uint32_t t_acc2 = t_acc1 + 256u;
-    uint32_t u = 0, tile_it = 0;
-    for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++tile_it) {
+    auto worker_bar = [] { asm volatile("bar.sync 1, %0;" ::"n"(Cfg::NWORK) : "memory"); };
+    const bool prof = (P.probe & 128) && wt == 0;
+    long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tp = 0;
+#define PHASE(i) do { if (prof) { long long _n = clock64(); pc[i] += _n - tp; tp = _n; } } while (0)
+    uint32_t u_tile = 0;
+    for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, u_tile += uses_per_tile) {
+      if (prof) tp = clock64();
       const int s_edge = tile * TC_TILE + r;
       const bool valid = s_edge < P.g.E;
       int my_row = -1, my_col = 0;
@@ -283,33 +324,38 @@ k_edge_layer_tc(const __grid_constant__ CUtensorMap wmap, const TcParams P) {
         else if (P.xt_lut) src = P.lut + ((P.xt_lut[P.g.perm ? P.g.perm[s_edge] : s_edge] != 0.0f) ? H : 0);
         else src = P.e + (size_t)s_edge * H;
       }
-      s_row[r] = my_row;
-      s_col[r] = my_col;
-      s_src[r] = src;
+      if (part == 0) {
+        s_row[r] = my_row;
+        s_src[r] = src;
+      }
       uint32_t seg_mask;
       {
         int next_row = __shfl_down_sync(0xffffffffu, my_row, 1);
         bool seg_end = valid && (lane == 31 || next_row != my_row);
         seg_mask = __ballot_sync(0xffffffffu, seg_end);
       }
-      __syncwarp();   // conversion below only reads this warp's own 32 rows of s_src
+      worker_bar();   // s_src / s_row of the whole tile visible to every worker
 
       // ---------------- GEMM1 A operand: fp32 edge rows -> bf16 hi/lo swizzled chunks ----------------
-      for (int kc = 0; kc < 4; ++kc, ++u) {
-        const int s = u & 1, k = u >> 1;
-        float4 x[16];
+      constexpr int CONV_IT = 16 / WPQ;
+      float4 xa[CONV_IT], xb[CONV_IT];
+      auto conv_load = [&](float4 (&x)[CONV_IT], int kc) {
 #pragma unroll
-        for (int it = 0; it < 16; ++it) {
-          const int rr = q * 32 + it * 2 + (lane >> 4);
-          x[it] = __ldg(reinterpret_cast<const float4*>(s_src[rr] + kc * TC_KCH) + (lane & 15));
+        for (int it = 0; it < CONV_IT; ++it) {
+          const int item = it * Cfg::NWORK + wt;
+          x[it] = __ldcg(reinterpret_cast<const float4*>(s_src[item >> 4] + kc * TC_KCH) + (item & 15));
         }
+      };
+      auto conv_store = [&](const float4 (&x)[CONV_IT], int kc) {
+        const uint32_t u = u_tile + kc;
+        const int s = u & 1, k = u >> 1;
         mbar_wait(&empty[s], (k & 1) ^ 1, P.error_flag, 4);
         unsigned char* a_hi = smem + s * TC_STAGE_BYTES;
         unsigned char* a_lo = a_hi + TC_A_BYTES;
 #pragma unroll
-        for (int it = 0; it < 16; ++it) {
-          const int rr = q * 32 + it * 2 + (lane >> 4);
-          const int k4 = lane & 15;
+        for (int it = 0; it < CONV_IT; ++it) {
+          const int item = it * Cfg::NWORK + wt;
+          const int rr = item >> 4, k4 = item & 15;
           uint2 hi, lo;
           split4(x[it], hi, lo);
           const uint32_t off = sw128_off(rr, k4 >> 1) + (k4 & 1) * 8;
@@ -318,21 +364,35 @@ k_edge_layer_tc(const __grid_constant__ CUtensorMap wmap, const TcParams P) {
         }
         fence_proxy_async();
         tc_fence_before();   // orders this thread's earlier TMEM reads (previous tile) before the MMA overwrites
-        mbar_arrive(&full_a[s]);
-      }
+        mbar_arrive(&full_a1[s]);
+      };
+      conv_load(xa, 0);
+      conv_load(xb, 1);
+      conv_store(xa, 0);
+      conv_load(xa, 2);
+      conv_store(xb, 1);
+      conv_load(xb, 3);
+      conv_store(xa, 2);
+      conv_store(xb, 3);
 
+      PHASE(0);   // setup + conversion
       // ---------------- E1: e_hat, gate, messages, row statistics ----------------
-      mbar_wait(&acc_rdy[0], tile_it & 1, P.error_flag, 5);
+      const uint32_t tile_par = (u_tile / uses_per_tile) & 1;
+      mbar_wait(&acc_rdy[0], tile_par, P.error_flag, 5);
       tc_fence_after();
+      PHASE(1);   // wait for GEMM1
       if (P.debug_acc) {
 #pragma unroll 1
-        for (int c0 = 0; c0 < H; c0 += 32) {
+        for (int c0 = cbase; c0 < cbase + Cfg::CPP; c0 += 32) {
           uint32_t v[32];
           tmem_ld32(t_acc1 + c0, v);
           tmem_wait_ld();
           if (valid) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) P.debug_acc[(size_t)s_edge * H + c0 + j] = __uint_as_float(v[j]);
+            for (int j = 0; j < 8; ++j)
+              __stcg(reinterpret_cast<float4*>(P.debug_acc + (size_t)s_edge * H + c0) + j,
+                     make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                 __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
           }
         }
         tc_fence_before();
@@ -345,48 +405,66 @@ k_edge_layer_tc(const __grid_constant__ CUtensorMap wmap, const TcParams P) {
       const size_t pair_base = (grp < P.g.n_groups) ? (size_t)P.g.grp_pair[grp] : 0;
       float K1 = 0.f, S1 = 0.f, Q1 = 0.f;
 #pragma unroll 1
-      for (int c0 = 0; c0 < H; c0 += 32) {
+      for (int c0 = cbase; c0 < cbase + Cfg::CPP; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(t_acc1 + c0, v);
         tmem_wait_ld();
         const float4* pa = reinterpret_cast<const float4*>(uv_col + 2 * H + c0);
         const float4* pb = reinterpret_cast<const float4*>(uv_row + 3 * H + c0);
         const float4* pv = reinterpret_cast<const float4*>(uv_col + H + c0);
+        float mm[32];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float4 a = __ldg(pa + j), b = __ldg(pb + j), vv = __ldg(pv + j);
+          float4 a, b, vv;
+          if (P.probe & 1) { a = b = vv = make_float4(0.1f, 0.2f, 0.3f, 0.4f); }
+          else { a = __ldg(pa + j); b = __ldg(pb + j); vv = __ldg(pv + j); }
           float xs[4] = {__uint_as_float(v[4 * j]) + a.x + b.x, __uint_as_float(v[4 * j + 1]) + a.y + b.y,
                          __uint_as_float(v[4 * j + 2]) + a.z + b.z, __uint_as_float(v[4 * j + 3]) + a.w + b.w};
           const float vs[4] = {vv.x, vv.y, vv.z, vv.w};
-          if (c0 == 0 && j == 0) K1 = xs[0];
+          if (c0 == cbase && j == 0) K1 = xs[0];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const float d = xs[i] - K1;
             S1 += d;
             Q1 = fmaf(d, d, Q1);
-            float m = sigmoidf_fast(xs[i]) * vs[i];
+            float m = sigmoid_mufu(xs[i]) * vs[i];
             if (!valid) m = (P.agg_mode == AGG_MAX) ? -INFINITY : 0.0f;
-            patch[lane * 33 + 4 * j + i] = m;
+            mm[4 * j + i] = m;
             v[4 * j + i] = __float_as_uint(xs[i]);
           }
         }
         if (P.write_e) tmem_st32(t_acc1 + c0, v);
-        __syncwarp();
-        // transposed pass: lane == column, walk the warp's 32 rows, flush at segment ends
-        {
-          float run = (P.agg_mode == AGG_MAX) ? -INFINITY : 0.0f;
+        // row-segment reduction of the messages: PATCH_COLS columns at a time are transposed through a
+        // per-warp patch ([column][row], stride 36: conflict-free both ways); lane == column pulls its 32 row
+        // values with 8 LDS.128 and sums the node segments in registers (seg_mask is warp-uniform).
 #pragma unroll
-          for (int rr = 0; rr < 32; ++rr) {
-            const float m = patch[rr * 33 + lane];
-            run = (P.agg_mode == AGG_MAX) ? fmaxf(run, m) : run + m;
-            if ((seg_mask >> rr) & 1u) {
-              const int node = s_row[q * 32 + rr];
-              P.partials[(pair_base + (size_t)(node - first_node)) * H + c0 + lane] = run;
-              run = (P.agg_mode == AGG_MAX) ? -INFINITY : 0.0f;
+        for (int sub = 0; sub < 32 / Cfg::PATCH_COLS; ++sub) {
+#pragma unroll
+          for (int cc = 0; cc < Cfg::PATCH_COLS; ++cc) patch[cc * 36 + lane] = mm[sub * Cfg::PATCH_COLS + cc];
+          __syncwarp();
+          if (lane < Cfg::PATCH_COLS) {
+            float mv[32];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 t4 = *reinterpret_cast<const float4*>(patch + lane * 36 + 4 * j);
+              mv[4 * j] = t4.x; mv[4 * j + 1] = t4.y; mv[4 * j + 2] = t4.z; mv[4 * j + 3] = t4.w;
+            }
+            uint32_t mask = seg_mask;
+            int start = 0;
+            while (mask) {                         // one iteration per node segment present in this warp
+              const int end = __ffs(mask) - 1;
+              mask &= mask - 1;
+              float run = (P.agg_mode == AGG_MAX) ? -INFINITY : 0.0f;
+#pragma unroll
+              for (int rr = 0; rr < 32; ++rr)
+                if (rr >= start && rr <= end) run = (P.agg_mode == AGG_MAX) ? fmaxf(run, mv[rr]) : run + mv[rr];
+              const int node = s_row[q * 32 + end];
+              P.partials[(pair_base + (size_t)(node - first_node)) * H + c0 + sub * Cfg::PATCH_COLS + lane] = run;
+              start = end + 1;
             }
           }
+          __syncwarp();
         }
-        __syncwarp();
       }
       if (!P.write_e) {   // MIS last layer: edge stream is dead (gnn_encoder.py:412)
         tmem_wait_ld();
@@ -394,37 +472,78 @@ k_edge_layer_tc(const __grid_constant__ CUtensorMap wmap, const TcParams P) {
         continue;
       }
       tmem_wait_st();
-      const float mean1 = K1 + S1 * (1.0f / H);
-      const float var1 = fmaxf(Q1 * (1.0f / H) - (S1 * (1.0f / H)) * (S1 * (1.0f / H)), 0.0f);
-      const float rstd1 = rsqrtf(var1 + LN_EPS);
+      float mean1, rstd1;
+      if constexpr (WPQ == 1) {
+        mean1 = K1 + S1 * (1.0f / H);
+        const float var1 = fmaxf(Q1 * (1.0f / H) - (S1 * (1.0f / H)) * (S1 * (1.0f / H)), 0.0f);
+        rstd1 = rsqrtf(var1 + LN_EPS);
+      } else {
+        stat1[part * TC_TILE + r] = make_float4(K1, S1, Q1, 0.f);
+        worker_bar();
+        float4 st[WPQ];
+        float msum = 0.f;
+#pragma unroll
+        for (int p2 = 0; p2 < WPQ; ++p2) {
+          st[p2] = stat1[p2 * TC_TILE + r];
+          msum += st[p2].x * (float)Cfg::CPP + st[p2].y;
+        }
+        mean1 = msum * (1.0f / H);
+        float ss = 0.f;   // sum (x - mean)^2 = sum_p [Q_p - 2 (mean - K_p) S_p + n_p (mean - K_p)^2]
+#pragma unroll
+        for (int p2 = 0; p2 < WPQ; ++p2) {
+          const float dk = mean1 - st[p2].x;
+          ss += st[p2].z - 2.0f * dk * st[p2].y + (float)Cfg::CPP * dk * dk;
+        }
+        rstd1 = rsqrtf(fmaxf(ss * (1.0f / H), 0.0f) + LN_EPS);
+      }
 
+      PHASE(2);   // E1 (+ stats exchange)
       // ---------------- E2: e_til = relu(LN_e(e_hat)) + tau, statistics for LN_O ----------------
-      float K2 = 0.f, S2 = 0.f, Q2 = 0.f;
+      float S2 = 0.f, Q2 = 0.f;   // e_til = relu(.)+tau is O(1) with mean ~ std: plain sums are safe in fp32
 #pragma unroll 1
-      for (int c0 = 0; c0 < H; c0 += 32) {
+      for (int c0 = cbase; c0 < cbase + Cfg::CPP; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(t_acc1 + c0, v);
         tmem_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int c = c0 + j;
-          float y = fmaxf(fmaf((__uint_as_float(v[j]) - mean1) * rstd1, prm[c], prm[H + c]), 0.0f) + prm[2 * H + c];
-          if (c == 0) K2 = y;
-          const float d = y - K2;
-          S2 += d;
-          Q2 = fmaf(d, d, Q2);
-          v[j] = __float_as_uint(y);
+        for (int j = 0; j < 8; ++j) {
+          const float4 g4 = *reinterpret_cast<const float4*>(prm + c0 + 4 * j);
+          const float4 b4 = *reinterpret_cast<const float4*>(prm + H + c0 + 4 * j);
+          const float4 t4 = *reinterpret_cast<const float4*>(prm + 2 * H + c0 + 4 * j);
+          const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+          const float tt[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float y = fmaxf(fmaf((__uint_as_float(v[4 * j + i]) - mean1) * rstd1, gg[i], bb[i]), 0.0f) + tt[i];
+            S2 += y;
+            Q2 = fmaf(y, y, Q2);
+            v[4 * j + i] = __float_as_uint(y);
+          }
         }
         tmem_st32(t_acc1 + c0, v);
       }
       tmem_wait_st();
-      const float mean2 = K2 + S2 * (1.0f / H);
-      const float var2 = fmaxf(Q2 * (1.0f / H) - (S2 * (1.0f / H)) * (S2 * (1.0f / H)), 0.0f);
+      if constexpr (WPQ > 1) {
+        stat2[part * TC_TILE + r] = make_float2(S2, Q2);
+        worker_bar();
+        S2 = 0.f;
+        Q2 = 0.f;
+#pragma unroll
+        for (int p2 = 0; p2 < WPQ; ++p2) {
+          const float2 t2 = stat2[p2 * TC_TILE + r];
+          S2 += t2.x;
+          Q2 += t2.y;
+        }
+      }
+      const float mean2 = S2 * (1.0f / H);
+      const float var2 = fmaxf(Q2 * (1.0f / H) - mean2 * mean2, 0.0f);
       const float rstd2 = rsqrtf(var2 + LN_EPS);
 
-      // ---------------- E3: s = silu(LN_O(e_til)) -> GEMM2 A operand chunks ----------------
+      PHASE(3);   // E2
+      // ---------------- E3: s = silu(LN_O(e_til)) -> GEMM2 A operand chunks (this part's K-chunks) ----------------
 #pragma unroll 1
-      for (int kc = 0; kc < 4; ++kc, ++u) {
+      for (int kc = part * (4 / WPQ); kc < (part + 1) * (4 / WPQ); ++kc) {
+        const uint32_t u = u_tile + 4 + kc;
         const int s = u & 1, k = u >> 1;
         unsigned char* a_hi = smem + s * TC_STAGE_BYTES;
         unsigned char* a_lo = a_hi + TC_A_BYTES;
@@ -439,10 +558,15 @@ k_edge_layer_tc(const __grid_constant__ CUtensorMap wmap, const TcParams P) {
           for (int j = 0; j < 4; ++j) {   // 4 x 16-byte units of 8 bf16
             float z[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int c = c0 + 8 * j + i;
-              const float t = fmaf((__uint_as_float(v[8 * j + i]) - mean2) * rstd2, prm[3 * H + c], prm[4 * H + c]);
-              z[i] = t * sigmoidf_fast(t);
+            for (int hh = 0; hh < 2; ++hh) {
+              const float4 g4 = *reinterpret_cast<const float4*>(prm + 3 * H + c0 + 8 * j + 4 * hh);
+              const float4 b4 = *reinterpret_cast<const float4*>(prm + 4 * H + c0 + 8 * j + 4 * hh);
+              const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float t = fmaf((__uint_as_float(v[8 * j + 4 * hh + i]) - mean2) * rstd2, gg[i], bb[i]);
+                z[4 * hh + i] = t * sigmoid_mufu(t);
+              }
             }
             uint2 h0, l0, h1, l1;
             split4(make_float4(z[0], z[1], z[2], z[3]), h0, l0);
@@ -454,35 +578,43 @@ k_edge_layer_tc(const __grid_constant__ CUtensorMap wmap, const TcParams P) {
         }
         fence_proxy_async();
         tc_fence_before();
-        mbar_arrive(&full_a[s]);
+        mbar_arrive(&full_a2[s]);
       }
 
-      // ---------------- E4: e = e_in + O(s) + b_O ----------------
-      mbar_wait(&acc_rdy[1], tile_it & 1, P.error_flag, 7);
+      PHASE(4);   // E3
+      // ---------------- E4: e = e_in + O(s) + b_O (this part's columns) ----------------
+      mbar_wait(&acc_rdy[1], tile_par, P.error_flag, 7);
       tc_fence_after();
+      PHASE(5);   // wait for GEMM2
 #pragma unroll 1
-      for (int c0 = 0; c0 < H; c0 += 32) {
+      for (int c0 = cbase; c0 < cbase + Cfg::CPP; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(t_acc2 + c0, v);
         tmem_wait_ld();
-        if (valid) {
+        if (valid && !(P.probe & 16)) {
           const float4* pin = reinterpret_cast<const float4*>(src + c0);
           float4* pout = reinterpret_cast<float4*>(P.e + (size_t)s_edge * H + c0);
+          float4 ein[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) ein[j] = __ldcg(pin + j);    // 8 independent loads in flight
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float4 ein = __ldg(pin + j);
+            const float4 bo = *reinterpret_cast<const float4*>(prm + 5 * H + c0 + 4 * j);
             float4 o;
-            o.x = ein.x + __uint_as_float(v[4 * j]) + prm[5 * H + c0 + 4 * j];
-            o.y = ein.y + __uint_as_float(v[4 * j + 1]) + prm[5 * H + c0 + 4 * j + 1];
-            o.z = ein.z + __uint_as_float(v[4 * j + 2]) + prm[5 * H + c0 + 4 * j + 2];
-            o.w = ein.w + __uint_as_float(v[4 * j + 3]) + prm[5 * H + c0 + 4 * j + 3];
-            pout[j] = o;
+            o.x = ein[j].x + __uint_as_float(v[4 * j]) + bo.x;
+            o.y = ein[j].y + __uint_as_float(v[4 * j + 1]) + bo.y;
+            o.z = ein[j].z + __uint_as_float(v[4 * j + 2]) + bo.z;
+            o.w = ein[j].w + __uint_as_float(v[4 * j + 3]) + bo.w;
+            __stcg(pout + j, o);
           }
         }
       }
       tc_fence_before();
-      __syncwarp();
+      PHASE(6);   // E4
     }
+    if (prof)
+      for (int i = 0; i < 7; ++i) atomicAdd(P.phase_cycles + i, (unsigned long long)pc[i]);
+#undef PHASE
   }
 
   // teardown
@@ -506,6 +638,8 @@ struct TcState {
   float* zero_row = nullptr;
   int* error_flag = nullptr;
   float* debug_acc = nullptr;   // set by the debug entry point for one launch
+  int wpq = 2;                  // worker warps per TMEM lane quarter (DFB_TC_WPQ, tuning knob)
+  unsigned long long* phase_cycles = nullptr;
 };
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -514,13 +648,24 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 
 inline int tc_init(TcState* st, int num_sms) {
   st->num_sms = num_sms;
-  cudaError_t e = cudaFuncSetAttribute(k_edge_layer_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_ALLOC);
+  cudaError_t e = cudaFuncSetAttribute(k_edge_layer_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<1>::SMEM_ALLOC);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(k_edge_layer_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<2>::SMEM_ALLOC);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(k_edge_layer_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<4>::SMEM_ALLOC);
   if (e != cudaSuccess) {
     st->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e);
     return -2;
   }
+  {
+    const char* w = getenv("DFB_TC_WPQ");
+    st->wpq = w ? atoi(w) : 2;
+    if (st->wpq != 1 && st->wpq != 2 && st->wpq != 4) st->wpq = 2;
+  }
   if ((e = cudaMalloc(&st->zero_row, H * sizeof(float))) != cudaSuccess ||
       (e = cudaMemset(st->zero_row, 0, H * sizeof(float))) != cudaSuccess ||
+      (e = cudaMalloc(&st->phase_cycles, 8 * sizeof(unsigned long long))) != cudaSuccess ||
+      (e = cudaMemset(st->phase_cycles, 0, 8 * sizeof(unsigned long long))) != cudaSuccess ||
       (e = cudaMalloc(&st->error_flag, sizeof(int))) != cudaSuccess ||
       (e = cudaMemset(st->error_flag, 0, sizeof(int))) != cudaSuccess) {
     st->err = std::string("tc_init alloc: ") + cudaGetErrorString(e);
@@ -532,6 +677,7 @@ inline int tc_init(TcState* st, int num_sms) {
 inline void tc_destroy(TcState* st) {
   if (st->zero_row) cudaFree(st->zero_row);
   if (st->error_flag) cudaFree(st->error_flag);
+  if (st->phase_cycles) cudaFree(st->phase_cycles);
   st->zero_row = nullptr;
   st->error_flag = nullptr;
 }
@@ -574,12 +720,19 @@ inline int tc_launch_edge_layer(TcState* st, int l, float* e, const float* uvab,
   P.e = e; P.uvab = uvab; P.partials = partials; P.g = g; P.lp = lp; P.tvec = tvec_edge;
   P.xt_lut = xt_lut; P.lut = lut; P.zero_row = st->zero_row; P.debug_acc = st->debug_acc;
   P.error_flag = st->error_flag;
+  P.phase_cycles = st->phase_cycles;
   P.write_e = st->debug_acc ? 0 : write_e;
   P.e_zero = e_zero; P.agg_mode = agg_mode;
   P.w_row_base = l * 4 * H;
   P.n_tiles = (g.E + TC_TILE - 1) / TC_TILE;
+  {
+    const char* pe = getenv("DFB_TC_PROBE");
+    P.probe = pe ? atoi(pe) : 0;
+  }
   int grid = P.n_tiles < st->num_sms ? P.n_tiles : st->num_sms;
-  k_edge_layer_tc<<<grid, TC_THREADS, TC_SMEM_ALLOC, stream>>>(st->wmap, P);
+  if (st->wpq == 1) k_edge_layer_tc<1><<<grid, TcCfg<1>::THREADS, TcCfg<1>::SMEM_ALLOC, stream>>>(st->wmap, P);
+  else if (st->wpq == 2) k_edge_layer_tc<2><<<grid, TcCfg<2>::THREADS, TcCfg<2>::SMEM_ALLOC, stream>>>(st->wmap, P);
+  else k_edge_layer_tc<4><<<grid, TcCfg<4>::THREADS, TcCfg<4>::SMEM_ALLOC, stream>>>(st->wmap, P);
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) {
     st->err = std::string("launch: ") + cudaGetErrorString(err);

@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(256) k_node_update(float* __restrict__ h, cons
                                                      const float* __restrict__ partials, GraphDev g,
                                                      const float* __restrict__ ln_g,
                                                      const float* __restrict__ ln_b,
-                                                     const float* __restrict__ tvec_or_null) {
+                                                     const float* __restrict__ tvec_or_null, int agg_mode) {
   int i = blockIdx.x * 8 + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
   if (i >= g.V) return;
@@ -150,12 +150,22 @@ __global__ void __launch_bounds__(256) k_node_update(float* __restrict__ h, cons
   }
   int e0 = g.rowptr[i], e1 = g.rowptr[i + 1];
   if (e1 > e0) {
+    // aggregation over the node's edges (gnn_encoder.py:184-191): sum (default) / mean / max of the
+    // per-group partial results, combined in ascending group order
+    float a8[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a8[j] = (agg_mode == 2) ? -INFINITY : 0.0f;
     for (int grp = e0 / GROUP; grp <= (e1 - 1) / GROUP; ++grp) {
       size_t pair = (size_t)g.grp_pair[grp] + (size_t)(i - g.grp_first[grp]);
       const float4* p = reinterpret_cast<const float4*>(partials + pair * H) + lane * 2;
       float4 a = p[0], b = p[1];
-      x[0] += a.x; x[1] += a.y; x[2] += a.z; x[3] += a.w; x[4] += b.x; x[5] += b.y; x[6] += b.z; x[7] += b.w;
+      const float pv[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a8[j] = (agg_mode == 2) ? fmaxf(a8[j], pv[j]) : a8[j] + pv[j];
     }
+    const float scale = (agg_mode == 1) ? 1.0f / (float)(e1 - e0) : 1.0f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] += (agg_mode == 1) ? a8[j] * scale : a8[j];
   }
   float s = 0.f;
 #pragma unroll

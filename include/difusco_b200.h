@@ -128,6 +128,9 @@ int dfb_profile_end(dfb_ctx* ctx, double* edge_kernel_ms, int64_t* edge_kernel_l
  * acc_out (E,256).  DEVICE pointers.  Used by the parity tests to localise failures. */
 int dfb_debug_edge_gemm(dfb_ctx* ctx, int layer, const float* e_in, float* acc_out, void* stream);
 
+/* Tuning hook: per-phase cycle counters of the tcgen05 edge kernel (DFB_TC_PROBE bit 7); out[8], host. */
+int dfb_debug_phase_cycles(dfb_ctx* ctx, unsigned long long* out);
+
 #ifdef __cplusplus
 }
 #endif

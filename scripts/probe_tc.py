@@ -1,0 +1,60 @@
+"""Timing probes of the fused edge-layer kernel on the BASELINE config[1] shape (not a bench)."""
+import os
+import sys
+import numpy as np
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+from difusco_b200 import synthetic as syn
+import gpu_util as G
+
+B = int(os.environ.get("PROBE_B", "16"))
+w = syn.make_encoder_weights(0, out_channels=2)
+pts, ei = syn.tsp_sparse_batch(500, 50, B, seed=1234)
+E = ei.shape[1]
+enc = G.encoder(w, 2, impl="tc")
+ctx = enc.set_graph(G.cu(ei), pts.shape[0], 1)
+enc.set_points(G.cu(pts))
+xt = G.cu((syn.initial_noise(E, 0) > 0).astype(np.float32))
+out = torch.empty((E, 2), device="cuda")
+st = torch.cuda.current_stream().cuda_stream
+
+
+def t_forward(tag):
+  ctx.encoder_forward(xt.data_ptr(), 500.0, out.data_ptr(), st)
+  torch.cuda.synchronize()
+  ctx.profile_begin()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e0.record()
+  ctx.encoder_forward(xt.data_ptr(), 500.0, out.data_ptr(), st)
+  e1.record()
+  torch.cuda.synchronize()
+  ms, n = ctx.profile_end()
+  print(f"{tag}: forward {e0.elapsed_time(e1):.2f} ms; edge kernel {ms / max(n, 1):.3f} ms/launch x{n}", flush=True)
+  if int(os.environ.get("DFB_TC_PROBE", "0")) & 128:
+    pc = ctx.debug_phase_cycles()
+    ntile_cta = (E + 127) // 128 * 12 * 2      # tiles x 12 layers x (warm-up + timed forward)
+    names = ["conv", "waitG1", "E1", "E2", "E3", "waitG2", "E4"]
+    print(f"{tag}: cycles/tile " + " ".join(f"{n}={c / ntile_cta:.0f}" for n, c in zip(names, pc)) +
+          f" total={sum(pc[:7]) / ntile_cta:.0f}", flush=True)
+
+
+def t_gemm(tag):
+  x = torch.randn(E, 256, device="cuda")
+  acc = torch.empty(E, 256, device="cuda")
+  ctx.debug_edge_gemm(1, x.data_ptr(), acc.data_ptr(), st)
+  torch.cuda.synchronize()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e0.record()
+  for _ in range(3):
+    ctx.debug_edge_gemm(1, x.data_ptr(), acc.data_ptr(), st)
+  e1.record()
+  torch.cuda.synchronize()
+  print(f"{tag}: GEMM1-only (convert + 48 MMA/tile + dump) {e0.elapsed_time(e1) / 3:.3f} ms/launch", flush=True)
+
+
+mode = sys.argv[1] if len(sys.argv) > 1 else "all"
+if mode in ("all", "gemm"):
+  t_gemm(f"probe={os.environ.get('DFB_TC_PROBE', '0')}")
+if mode in ("all", "fwd"):
+  t_forward(f"probe={os.environ.get('DFB_TC_PROBE', '0')}")
