@@ -181,7 +181,7 @@ class Context(object):
     return ms.value, n.value
 
   def debug_phase_cycles(self):
-    out = (C.c_uint64 * 8)()
+    out = (C.c_uint64 * 16)()
     self._ck(lib().dfb_debug_phase_cycles(self._h, out))
     return [int(x) for x in out]
 

@@ -257,7 +257,7 @@ extern "C" int dfb_load_weights(dfb_ctx* ctx, int n_layers, int hidden_dim, int 
     size_t Wt_uvab, b_uvab, Wt_C, Wt_O, b_O, hg, hb, eg, eb, og, ob, Wt_tau, b_tau;
   };
   std::vector<LOff> lo(L);
-  std::vector<uint16_t> arena16((size_t)L * 4 * H * H);
+  std::vector<uint16_t> arena16((size_t)L * 12 * H * H);
   const float* p;
   for (int l = 0; l < L; ++l) {
     std::string pre = "layers." + std::to_string(l) + ".";
@@ -292,7 +292,7 @@ extern "C" int dfb_load_weights(dfb_ctx* ctx, int n_layers, int hidden_dim, int 
     GET(pt + "weight", H * TE, &p); lo[l].Wt_tau = put_T(p, H, TE);
     GET(pt + "bias", H, &p);        lo[l].b_tau = put_v(p, H);
     // bf16 hi/lo split of C and O, [out][in] K-major (the tensor-core B operand)
-    uint16_t* a16 = &arena16[(size_t)l * 4 * H * H];
+    uint16_t* a16 = &arena16[(size_t)l * 12 * H * H];
     for (int i = 0; i < H * H; ++i) {
       uint16_t hi = f2bf16_rn(WC[i]);
       a16[i] = hi;
@@ -300,6 +300,11 @@ extern "C" int dfb_load_weights(dfb_ctx* ctx, int n_layers, int hidden_dim, int 
       hi = f2bf16_rn(WO[i]);
       a16[2 * H * H + i] = hi;
       a16[3 * H * H + i] = f2bf16_rn(WO[i] - bf16_to_f(hi));
+      for (int qq = 0; qq < 4; ++qq) {   // U, V, A, B: [out][in] K-major, hi then lo
+        hi = f2bf16_rn(W[qq][i]);
+        a16[(size_t)(4 + 2 * qq) * H * H + i] = hi;
+        a16[(size_t)(5 + 2 * qq) * H * H + i] = f2bf16_rn(W[qq][i] - bf16_to_f(hi));
+      }
     }
   }
   size_t o_node_W, o_node_b, o_edge_W, o_edge_b, o_t0W, o_t0b, o_t2W, o_t2b, o_gng, o_gnb, o_outW, o_outb;
@@ -351,7 +356,7 @@ extern "C" int dfb_load_weights(dfb_ctx* ctx, int n_layers, int hidden_dim, int 
     lp.ln_e_g = base + lo[l].eg; lp.ln_e_b = base + lo[l].eb;
     lp.ln_o_g = base + lo[l].og; lp.ln_o_b = base + lo[l].ob;
     lp.Wt_tau = base + lo[l].Wt_tau; lp.b_tau = base + lo[l].b_tau;
-    lp.C_hi = base16 + (size_t)l * 4 * H * H; lp.C_lo = lp.C_hi + H * H;
+    lp.C_hi = base16 + (size_t)l * 12 * H * H; lp.C_lo = lp.C_hi + H * H;
     lp.O_hi = lp.C_hi + 2 * H * H;            lp.O_lo = lp.C_hi + 3 * H * H;
   }
   CK(ctx, cudaMemcpy(ctx->layers_dev.p, ctx->layers.data(), L * sizeof(LayerParams), cudaMemcpyHostToDevice));
@@ -503,6 +508,20 @@ extern "C" int dfb_prepare_graph(dfb_ctx* ctx, const int64_t* edge_index, int64_
   return DFB_OK;
 }
 
+// node-side linears h -> [U|V|A|B] h of layer l: tensor-core path (product) or fp32 FFMA (validation impl)
+static int node_linears(dfb_ctx* ctx, int l, const float* h, float* uvab, int V, cudaStream_t st) {
+  if (ctx->edge_impl == DFB_EDGE_IMPL_FP32) {
+    dim3 grid((V + LIN_ROWS - 1) / LIN_ROWS, 4);
+    k_linear<<<grid, 256, 0, st>>>(h, ctx->layers[l].Wt_uvab, ctx->layers[l].b_uvab, uvab, V, 4 * H);
+    CKL(ctx);
+    return DFB_OK;
+  }
+  int r = tc_launch_linear(&ctx->tc, l, h, uvab, ctx->layers[l].b_uvab, V, ctx->g, ctx->layers[l], st);
+  if (r) FAIL(ctx, DFB_E_CUDA, "tcgen05 node linear: %s", ctx->tc.err.c_str());
+  ctx->launches += 1;
+  return DFB_OK;
+}
+
 // rows X[R][256] -> Y = X Wt + b through the generic linear, chunked features
 static int linear_rows(dfb_ctx* ctx, const float* X, const float* Wt, const float* b, float* Y, int R, int N,
                        cudaStream_t st) {
@@ -535,8 +554,7 @@ extern "C" int dfb_set_points(dfb_ctx* ctx, const float* points, void* stream_) 
     if (r) return r;
   }
   // layer 0's node linears are step-invariant too
-  int r = linear_rows(ctx, (const float*)ctx->h0.p, ctx->layers[0].Wt_uvab, ctx->layers[0].b_uvab,
-                      (float*)ctx->uvab0.p, V, 4 * H, st);
+  int r = node_linears(ctx, 0, (const float*)ctx->h0.p, (float*)ctx->uvab0.p, V, st);
   if (r) return r;
   ctx->points_ready = true;
   return DFB_OK;
@@ -624,7 +642,7 @@ static int run_forward(dfb_ctx* ctx, const float* xt, const float* tvec, bool bi
     if (l == 0 && !ctx->node_only) {
       uv = (const float*)ctx->uvab0.p;
     } else {
-      int r = linear_rows(ctx, h, ctx->layers[l].Wt_uvab, ctx->layers[l].b_uvab, uvab, V, 4 * H, st);
+      int r = node_linears(ctx, l, h, uvab, V, st);
       if (r) return r;
     }
     const float* tv = tvec + (size_t)l * H;
@@ -645,9 +663,9 @@ static int run_forward(dfb_ctx* ctx, const float* xt, const float* tvec, bool bi
   const int bps = (rps + GN_ROWS_PER_BLOCK - 1) / GN_ROWS_PER_BLOCK;
   k_gn_partial<<<dim3(bps, ctx->gn_segments), 256, 0, st>>>(Z, rps, (double*)ctx->gn_part.p);
   CKL(ctx);
-  k_gn_final<<<ctx->gn_segments, 32, 0, st>>>((const double*)ctx->gn_part.p, bps, rps, (float*)ctx->gn_stats.p);
+  k_gn_final<<<ctx->gn_segments, 1024, 0, st>>>((const double*)ctx->gn_part.p, bps, rps, (float*)ctx->gn_stats.p);
   CKL(ctx);
-  k_head<<<(R + 7) / 8, 256, 0, st>>>(Z, R, rps, (const float*)ctx->gn_stats.p, ctx->node_only ? nullptr : g.perm,
+  k_head<<<(R + 255) / 256, 256, 0, st>>>(Z, R, rps, (const float*)ctx->gn_stats.p, ctx->node_only ? nullptr : g.perm,
                                       ctx->hp, pa);
   CKL(ctx);
   return DFB_OK;
@@ -811,7 +829,7 @@ extern "C" int dfb_debug_phase_cycles(dfb_ctx* ctx, unsigned long long* out) {
   if (!ctx || !out) return DFB_E_INVALID;
   CK(ctx, cudaSetDevice(ctx->device));
   CK(ctx, cudaDeviceSynchronize());
-  CK(ctx, cudaMemcpy(out, ctx->tc.phase_cycles, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-  CK(ctx, cudaMemset(ctx->tc.phase_cycles, 0, 8 * sizeof(unsigned long long)));
+  CK(ctx, cudaMemcpy(out, ctx->tc.phase_cycles, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  CK(ctx, cudaMemset(ctx->tc.phase_cycles, 0, 16 * sizeof(unsigned long long)));
   return DFB_OK;
 }

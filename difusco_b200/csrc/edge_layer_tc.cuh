@@ -34,7 +34,10 @@ constexpr int TC_TILE = 128;
 constexpr int TC_KCH = 64;                         // K elements per chunk = one 128-byte swizzle row
 constexpr int TC_A_BYTES = TC_TILE * 128;          // 16 KB  (hi or lo)
 constexpr int TC_B_BYTES = 256 * 128;              // 32 KB  (hi or lo)
-constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;   // 96 KB
+constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;   // 96 KB per stage, laid out A0 | A1 | B0 | B1
+__host__ __device__ constexpr int tc_off_a(int s) { return s * 2 * TC_A_BYTES; }
+__host__ __device__ constexpr int tc_off_b(int s) { return 4 * TC_A_BYTES + s * 2 * TC_B_BYTES; }
+constexpr int TC_BOX_BYTES = TC_TILE * 128;        // one fp32 [128 rows x 32 cols] TMA box of the edge stream
 constexpr int TC_NSTAGE = 2;
 constexpr int TC_OFF_PRM = TC_NSTAGE * TC_STAGE_BYTES;            // 6 x 256 floats
 // UMMA instruction descriptor: D=F32, A=B=BF16, both K-major, N=256, M=128 (cute::UMMA::InstrDescriptor)
@@ -51,11 +54,17 @@ struct TcParams {
   const float* lut;       // [2][256]
   const float* zero_row;  // [256] zeros
   float* debug_acc;       // tests: dump GEMM1 accumulator [E][256] and stop
+  // linear mode (node-side linears on the same tensor-core path): rows of lin_in [lin_rows][256] times the four
+  // 256x256 blocks U|V|A|B -> lin_out [lin_rows][1024] (+ lin_bias[1024]).  tile = row_tile * 4 + block.
+  const float* lin_in;
+  float* lin_out;
+  const float* lin_bias;
+  int lin_rows;
   int* error_flag;
   int write_e, e_zero, agg_mode;
   int w_row_base;         // row of this layer's C_hi block in the bf16 weight arena tensor map
   int n_tiles;
-  unsigned long long* phase_cycles;   // [8] probe bit 7: per-phase cycle sums of worker thread 0, all CTAs
+  unsigned long long* phase_cycles;   // [16] probe bit 7: per-phase cycle sums of worker thread 0, all CTAs
   int probe;   // timing experiments only (DFB_TC_PROBE env): bit0 no gathers, bit1 no segment reduce, bit2 no E2,
                // bit3 no E3 math, bit4 no E4 load/store, bit5 no conversion loads, bit6 no sigmoid
 };
@@ -150,6 +159,42 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
       ::TC_W32(v), "r"(taddr)
       : "memory");
 }
+#define TC_R16(v) \
+  "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),       \
+  "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+#define TC_W16(v) \
+  "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),     \
+  "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : TC_R16(v)
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15};"
+      ::TC_W16(v), "r"(taddr)
+      : "memory");
+}
+// Ampere-style 16-byte async copy global -> shared (LDGSTS): coalesced gathers without register staging
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// TMA store smem -> global (bulk async-group completion)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
@@ -182,15 +227,17 @@ __device__ __forceinline__ uint32_t sw128_off(int r, int j) {
 // LayerNorm partial statistics of the slices are combined through shared memory.
 template <int WPQ>
 struct TcCfg {
+  static_assert(WPQ == 1 || WPQ == 2, "1 or 2 worker warps per TMEM lane quarter");
   static constexpr int NWORK = 128 * WPQ;                 // worker threads
   static constexpr int THREADS = 64 + NWORK;
   static constexpr int CPP = H / WPQ;                     // columns per part
-  static constexpr int PATCH_COLS = (WPQ == 4) ? 4 : 32 / WPQ;
+  static constexpr int PATCH_COLS = 16;                   // E1 works in 16-column sub-chunks
   static constexpr int OFF_PATCH = TC_OFF_PRM + 6 * H * 4;
   static constexpr int OFF_STAT1 = OFF_PATCH + 4 * WPQ * PATCH_COLS * 36 * 4;
   static constexpr int OFF_STAT2 = OFF_STAT1 + WPQ * TC_TILE * 16;
   static constexpr int OFF_ROW = OFF_STAT2 + WPQ * TC_TILE * 8;
-  static constexpr int OFF_SRC = OFF_ROW + TC_TILE * 4;
+  static constexpr int OFF_COL = OFF_ROW + TC_TILE * 4;
+  static constexpr int OFF_SRC = OFF_COL + TC_TILE * 4;
   static constexpr int OFF_BAR = OFF_SRC + TC_TILE * 8;
   static constexpr int SMEM_BYTES = OFF_BAR + 128;
   static constexpr int SMEM_ALLOC = SMEM_BYTES + 1024;    // slack for 1024-byte alignment
@@ -199,7 +246,8 @@ struct TcCfg {
 
 template <int WPQ>
 __global__ void __launch_bounds__(TcCfg<WPQ>::THREADS, 1)
-k_edge_layer_tc(const __grid_constant__ CUtensorMap wmap, const TcParams P) {
+k_edge_layer_tc(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap emap,
+                const TcParams P) {
   using Cfg = TcCfg<WPQ>;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays in .shared
@@ -208,6 +256,7 @@ k_edge_layer_tc(const __grid_constant__ CUtensorMap wmap, const TcParams P) {
   float4* stat1 = reinterpret_cast<float4*>(smem + Cfg::OFF_STAT1);   // [WPQ][128] (K, S, Q, -)
   float2* stat2 = reinterpret_cast<float2*>(smem + Cfg::OFF_STAT2);   // [WPQ][128] (S, Q)
   int* s_row = reinterpret_cast<int*>(smem + Cfg::OFF_ROW);
+  int* s_col = reinterpret_cast<int*>(smem + Cfg::OFF_COL);
   const float** s_src = reinterpret_cast<const float**>(smem + Cfg::OFF_SRC);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
   uint64_t* full_a1 = bars;       // [2] all workers -> MMA (GEMM1 A chunks, NWORK arrivals)
@@ -215,7 +264,9 @@ k_edge_layer_tc(const __grid_constant__ CUtensorMap wmap, const TcParams P) {
   uint64_t* full_b = bars + 4;    // [2] TMA -> MMA (expect_tx)
   uint64_t* empty = bars + 6;     // [2] MMA commit -> producer + workers
   uint64_t* acc_rdy = bars + 8;   // [2] MMA commit -> workers (GEMM1 / GEMM2 accumulator complete)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* ein_bar = bars + 10;  // TMA load of the residual tile (expect_tx)
+  uint64_t* e4_done = bars + 11;  // staging (A0|A1|B0) released after the TMA store has read it
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int uses_per_tile = P.write_e ? 8 : 4;
@@ -226,6 +277,7 @@ k_edge_layer_tc(const __grid_constant__ CUtensorMap wmap, const TcParams P) {
     mbar_init(&full_b[0], 1);           mbar_init(&full_b[1], 1);
     mbar_init(&empty[0], 1);            mbar_init(&empty[1], 1);
     mbar_init(&acc_rdy[0], 1);          mbar_init(&acc_rdy[1], 1);
+    mbar_init(ein_bar, 1);              mbar_init(e4_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_proxy_async();
   }
@@ -251,9 +303,11 @@ k_edge_layer_tc(const __grid_constant__ CUtensorMap wmap, const TcParams P) {
   if (warp == 0) {
     // ===================================== TMA producer =====================================
     if (lane == 0) {
-      uint32_t u = 0;
-      for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
-        if (!P.e_zero && !P.xt_lut && tile + (int)gridDim.x < P.n_tiles && !(P.probe & 256)) {
+      uint32_t u = 0, tile_it = 0;
+      for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++tile_it) {
+        // E4 of the previous tile stages its output in A0|A1|B0: do not refill B0 before the store has read it
+        if (P.write_e && tile_it > 0) mbar_wait(e4_done, (tile_it - 1) & 1, P.error_flag, 8);
+        if (!P.lin_out && !P.e_zero && !P.xt_lut && tile + (int)gridDim.x < P.n_tiles && !(P.probe & 256)) {
           // the next tile's 128 edge rows are one contiguous 128 KB block: pull it into L2 now
           const float* nxt = P.e + (size_t)(tile + gridDim.x) * TC_TILE * H;
           asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nxt), "r"(TC_TILE * H * 4) : "memory");
@@ -262,10 +316,14 @@ k_edge_layer_tc(const __grid_constant__ CUtensorMap wmap, const TcParams P) {
           const int s = u & 1, k = u >> 1, kc = i & 3;
           mbar_wait(&empty[s], (k & 1) ^ 1, P.error_flag, 1);
           mbar_arrive_expect_tx(&full_b[s], 2 * TC_B_BYTES);
-          const uint32_t dst = smem_base + s * TC_STAGE_BYTES + 2 * TC_A_BYTES;
-          const int rb = P.w_row_base + (i < 4 ? 0 : 512);   // C_hi,C_lo | O_hi,O_lo blocks of 256 rows
-          tma_load_2d(dst, &wmap, &full_b[s], kc * TC_KCH, rb);
-          tma_load_2d(dst + TC_B_BYTES, &wmap, &full_b[s], kc * TC_KCH, rb + 256);
+          const uint32_t dst = smem_base + tc_off_b(s);
+          // C_hi,C_lo | O_hi,O_lo blocks of 256 rows; linear mode: U|V|A|B (hi,lo) blocks follow at +1024
+          const int rb = P.lin_out ? P.w_row_base + 1024 + (tile & 3) * 512 : P.w_row_base + (i < 4 ? 0 : 512);
+          // GEMM2 consumes its K-chunks in the order 0,2,1,3 so that with two column parts (chunks {0,1} and {2,3})
+          // both parts' first chunks feed the tensor core while E3 is still producing the second ones
+          const int kw = (i >= 4 && !P.lin_out) ? ((kc & 1) * 2 + (kc >> 1)) : kc;
+          tma_load_2d(dst, &wmap, &full_b[s], kw * TC_KCH, rb);
+          tma_load_2d(dst + TC_B_BYTES, &wmap, &full_b[s], kw * TC_KCH, rb + 256);
         }
       }
     }
@@ -280,8 +338,8 @@ k_edge_layer_tc(const __grid_constant__ CUtensorMap wmap, const TcParams P) {
           // each A barrier of a stage completes twice per tile (chunks kc, kc+2): parity (kc>>1)&1
           mbar_wait(i < 4 ? &full_a1[s] : &full_a2[s], (kc >> 1) & 1, P.error_flag, 3);
           tc_fence_after();
-          const uint32_t a_hi = smem_base + s * TC_STAGE_BYTES, a_lo = a_hi + TC_A_BYTES;
-          const uint32_t b_hi = a_hi + 2 * TC_A_BYTES, b_lo = b_hi + TC_B_BYTES;
+          const uint32_t a_hi = smem_base + tc_off_a(s), a_lo = a_hi + TC_A_BYTES;
+          const uint32_t b_hi = smem_base + tc_off_b(s), b_lo = b_hi + TC_B_BYTES;
           const uint32_t d = tmem_base + (i < 4 ? 0u : 256u);
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
@@ -308,16 +366,19 @@ k_edge_layer_tc(const __grid_constant__ CUtensorMap wmap, const TcParams P) {
     const uint32_t t_acc2 = t_acc1 + 256u;
     auto worker_bar = [] { asm volatile("bar.sync 1, %0;" ::"n"(Cfg::NWORK) : "memory"); };
     const bool prof = (P.probe & 128) && wt == 0;
-    long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tp = 0;
+    long long pc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tp = 0, tq = 0;
+#define SUBPH(i) do { if (prof) { long long _n = clock64(); pc[i] += _n - tq; tq = _n; } } while (0)
 #define PHASE(i) do { if (prof) { long long _n = clock64(); pc[i] += _n - tp; tp = _n; } } while (0)
     uint32_t u_tile = 0;
     for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, u_tile += uses_per_tile) {
       if (prof) tp = clock64();
-      const int s_edge = tile * TC_TILE + r;
-      const bool valid = s_edge < P.g.E;
+      const int s_edge = (P.lin_out ? (tile >> 2) : tile) * TC_TILE + r;
+      const bool valid = s_edge < (P.lin_out ? P.lin_rows : P.g.E);
       int my_row = -1, my_col = 0;
       const float* src = P.zero_row;
-      if (valid) {
+      if (valid && P.lin_out) {
+        src = P.lin_in + (size_t)s_edge * H;
+      } else if (valid) {
         my_row = P.g.row[s_edge];
         my_col = P.g.col[s_edge];
         if (P.e_zero) src = P.zero_row;
@@ -326,6 +387,7 @@ k_edge_layer_tc(const __grid_constant__ CUtensorMap wmap, const TcParams P) {
       }
       if (part == 0) {
         s_row[r] = my_row;
+        s_col[r] = my_col;
         s_src[r] = src;
       }
       uint32_t seg_mask;
@@ -350,7 +412,7 @@ k_edge_layer_tc(const __grid_constant__ CUtensorMap wmap, const TcParams P) {
         const uint32_t u = u_tile + kc;
         const int s = u & 1, k = u >> 1;
         mbar_wait(&empty[s], (k & 1) ^ 1, P.error_flag, 4);
-        unsigned char* a_hi = smem + s * TC_STAGE_BYTES;
+        unsigned char* a_hi = smem + tc_off_a(s);
         unsigned char* a_lo = a_hi + TC_A_BYTES;
 #pragma unroll
         for (int it = 0; it < CONV_IT; ++it) {
@@ -368,6 +430,8 @@ k_edge_layer_tc(const __grid_constant__ CUtensorMap wmap, const TcParams P) {
       };
       conv_load(xa, 0);
       conv_load(xb, 1);
+      // the previous tile's TMA store must have finished reading the staging area (A0|A1|B0)
+      if (P.write_e && u_tile > 0) mbar_wait(e4_done, ((u_tile / uses_per_tile) - 1) & 1, P.error_flag, 9);
       conv_store(xa, 0);
       conv_load(xa, 2);
       conv_store(xb, 1);
@@ -381,6 +445,27 @@ k_edge_layer_tc(const __grid_constant__ CUtensorMap wmap, const TcParams P) {
       mbar_wait(&acc_rdy[0], tile_par, P.error_flag, 5);
       tc_fence_after();
       PHASE(1);   // wait for GEMM1
+      if (P.lin_out) {
+        const int nb = tile & 3;
+#pragma unroll 1
+        for (int c0 = cbase; c0 < cbase + Cfg::CPP; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(t_acc1 + c0, v);
+          tmem_wait_ld();
+          if (valid) {
+            const float4* bias = reinterpret_cast<const float4*>(P.lin_bias + nb * H + c0);
+            float4* dst = reinterpret_cast<float4*>(P.lin_out + (size_t)s_edge * 4 * H + nb * H + c0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b4 = __ldg(bias + j);
+              __stcg(dst + j, make_float4(__uint_as_float(v[4 * j]) + b4.x, __uint_as_float(v[4 * j + 1]) + b4.y,
+                                          __uint_as_float(v[4 * j + 2]) + b4.z, __uint_as_float(v[4 * j + 3]) + b4.w));
+            }
+          }
+        }
+        tc_fence_before();
+        continue;
+      }
       if (P.debug_acc) {
 #pragma unroll 1
         for (int c0 = cbase; c0 < cbase + Cfg::CPP; c0 += 32) {
@@ -398,30 +483,76 @@ k_edge_layer_tc(const __grid_constant__ CUtensorMap wmap, const TcParams P) {
         tc_fence_before();
         continue;
       }
-      const float* uv_col = P.uvab + (size_t)my_col * 4 * H;
       const float* uv_row = P.uvab + (size_t)(valid ? my_row : 0) * 4 * H;
       const int grp = tile * 4 + q;
       const int first_node = (grp < P.g.n_groups) ? P.g.grp_first[grp] : 0;
       const size_t pair_base = (grp < P.g.n_groups) ? (size_t)P.g.grp_pair[grp] : 0;
+      // A h[col] and V h[col] are gathered with coalesced 16-byte cp.async (lanes along channels) into
+      // 128B-swizzled staging rows [A 16 cols | V 16 cols]; the stage-A operand memory is idle during E1.
+      // Every warp stages only its own 32 rows (two 4 KB buffers: sub-chunk i+1 in flight while i is consumed),
+      // so __syncwarp is the only synchronisation.  TMEM data and the B h[row] values of the next sub-chunk are
+      // prefetched into registers.
+      unsigned char* gbuf0 = smem + tc_off_a(part) + q * 8192;
+      unsigned char* gbuf1 = gbuf0 + 4096;
+      // lane handles piece (lane & 7) of rows (it*4 + lane/8): source pointers / smem offsets are fixed per tile
+      const float* gptr[8];
+      uint32_t goff[8];
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int row = it * 4 + (lane >> 3), piece = lane & 7;
+        gptr[it] = P.uvab + (size_t)s_col[q * 32 + row] * 4 * H + ((piece < 4) ? 2 * H : H) + cbase + 4 * (piece & 3);
+        goff[it] = sw128_off(row, piece);
+      }
+      auto gather_issue = [&](int sub, unsigned char* buf) {
+        const uint32_t b32 = smem_u32(buf);
+#pragma unroll
+        for (int it = 0; it < 8; ++it) cp_async16(b32 + goff[it], gptr[it] + sub * 16);
+        cp_async_commit();
+      };
+      constexpr int NSUB = Cfg::CPP / 16;
+      gather_issue(0, gbuf0);
+      gather_issue(1, gbuf1);
+      const float4* pb = reinterpret_cast<const float4*>(uv_row + 3 * H + cbase);
+      uint32_t vn[16];
+      float4 bn[4];
+      tmem_ld16(t_acc1 + cbase, vn);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bn[j] = __ldg(pb + j);
       float K1 = 0.f, S1 = 0.f, Q1 = 0.f;
 #pragma unroll 1
-      for (int c0 = cbase; c0 < cbase + Cfg::CPP; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(t_acc1 + c0, v);
+      for (int sub = 0; sub < NSUB; ++sub) {
+        const int c0 = cbase + sub * 16;
+        unsigned char* buf = (sub & 1) ? gbuf1 : gbuf0;
+        uint32_t v[16];
+        float4 bb[4];
+        if (prof) tq = clock64();
         tmem_wait_ld();
-        const float4* pa = reinterpret_cast<const float4*>(uv_col + 2 * H + c0);
-        const float4* pb = reinterpret_cast<const float4*>(uv_row + 3 * H + c0);
-        const float4* pv = reinterpret_cast<const float4*>(uv_col + H + c0);
-        float mm[32];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float4 a, b, vv;
-          if (P.probe & 1) { a = b = vv = make_float4(0.1f, 0.2f, 0.3f, 0.4f); }
-          else { a = __ldg(pa + j); b = __ldg(pb + j); vv = __ldg(pv + j); }
+        for (int j = 0; j < 16; ++j) v[j] = vn[j];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bb[j] = bn[j];
+        if (sub + 1 < NSUB) {               // prefetch the next sub-chunk
+          tmem_ld16(t_acc1 + c0 + 16, vn);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) bn[j] = __ldg(pb + 4 * (sub + 1) + j);
+        }
+        SUBPH(8);                           // tmem wait + prefetch issue
+        if (sub + 1 < NSUB) cp_async_wait<1>(); else cp_async_wait<0>();
+        __syncwarp();                       // this warp's pieces of the sub-chunk have landed
+        SUBPH(9);                           // gather wait
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float4 a, vv;
+          if (P.probe & 1) { a = vv = make_float4(0.1f, 0.2f, 0.3f, 0.4f); }
+          else {
+            a = *reinterpret_cast<const float4*>(buf + sw128_off(lane, j));
+            vv = *reinterpret_cast<const float4*>(buf + sw128_off(lane, 4 + j));
+          }
+          const float4 b = bb[j];
           float xs[4] = {__uint_as_float(v[4 * j]) + a.x + b.x, __uint_as_float(v[4 * j + 1]) + a.y + b.y,
                          __uint_as_float(v[4 * j + 2]) + a.z + b.z, __uint_as_float(v[4 * j + 3]) + a.w + b.w};
           const float vs[4] = {vv.x, vv.y, vv.z, vv.w};
-          if (c0 == cbase && j == 0) K1 = xs[0];
+          if (sub == 0 && j == 0) K1 = xs[0];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const float d = xs[i] - K1;
@@ -429,42 +560,66 @@ k_edge_layer_tc(const __grid_constant__ CUtensorMap wmap, const TcParams P) {
             Q1 = fmaf(d, d, Q1);
             float m = sigmoid_mufu(xs[i]) * vs[i];
             if (!valid) m = (P.agg_mode == AGG_MAX) ? -INFINITY : 0.0f;
-            mm[4 * j + i] = m;
+            patch[(4 * j + i) * 36 + lane] = m;   // transposed [column][row]: conflict-free (4c + lane)
             v[4 * j + i] = __float_as_uint(xs[i]);
           }
         }
-        if (P.write_e) tmem_st32(t_acc1 + c0, v);
-        // row-segment reduction of the messages: PATCH_COLS columns at a time are transposed through a
-        // per-warp patch ([column][row], stride 36: conflict-free both ways); lane == column pulls its 32 row
-        // values with 8 LDS.128 and sums the node segments in registers (seg_mask is warp-uniform).
+        if (P.write_e) tmem_st16(t_acc1 + c0, v);
+        __syncwarp();                       // buffer consumed, patch complete
+        SUBPH(10);                          // math
+        if (sub + 2 < NSUB) gather_issue(sub + 2, buf);
+        SUBPH(11);                          // gather issue
+        // row-segment reduction: lane = (column c = lane & 15, row half = lane >> 4) sums its 16 rows of every
+        // node segment from the transposed patch, halves are combined with one shuffle; seg_mask is
+        // warp-uniform; partial rows leave as coalesced stores
+        {
+          const float* pcol = patch + (lane & 15) * 36;
+          const int r_lo = (lane >> 4) * 16, r_hi = r_lo + 15;
+          float mv[16];
 #pragma unroll
-        for (int sub = 0; sub < 32 / Cfg::PATCH_COLS; ++sub) {
-#pragma unroll
-          for (int cc = 0; cc < Cfg::PATCH_COLS; ++cc) patch[cc * 36 + lane] = mm[sub * Cfg::PATCH_COLS + cc];
-          __syncwarp();
-          if (lane < Cfg::PATCH_COLS) {
-            float mv[32];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 t4 = *reinterpret_cast<const float4*>(patch + lane * 36 + 4 * j);
-              mv[4 * j] = t4.x; mv[4 * j + 1] = t4.y; mv[4 * j + 2] = t4.z; mv[4 * j + 3] = t4.w;
-            }
-            uint32_t mask = seg_mask;
-            int start = 0;
-            while (mask) {                         // one iteration per node segment present in this warp
-              const int end = __ffs(mask) - 1;
-              mask &= mask - 1;
-              float run = (P.agg_mode == AGG_MAX) ? -INFINITY : 0.0f;
-#pragma unroll
-              for (int rr = 0; rr < 32; ++rr)
-                if (rr >= start && rr <= end) run = (P.agg_mode == AGG_MAX) ? fmaxf(run, mv[rr]) : run + mv[rr];
-              const int node = s_row[q * 32 + end];
-              P.partials[(pair_base + (size_t)(node - first_node)) * H + c0 + sub * Cfg::PATCH_COLS + lane] = run;
-              start = end + 1;
-            }
+          for (int j = 0; j < 4; ++j) {
+            const float4 t4 = *reinterpret_cast<const float4*>(pcol + r_lo + 4 * j);
+            mv[4 * j] = t4.x; mv[4 * j + 1] = t4.y; mv[4 * j + 2] = t4.z; mv[4 * j + 3] = t4.w;
           }
-          __syncwarp();
+          uint32_t mask = seg_mask;
+          int start = 0;
+          while (mask) {                         // one iteration per node segment present in this warp
+            const int end = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const int lo = max(start, r_lo) - r_lo, hi = min(end, r_hi) - r_lo;   // my 16 rows of this segment
+            const uint32_t rm = (hi >= lo) ? (((2u << hi) - 1u) & ~((1u << lo) - 1u)) : 0u;
+            float run;
+            if (P.agg_mode == AGG_MAX) {
+              float r0 = -INFINITY, r1 = -INFINITY;
+#pragma unroll
+              for (int i = 0; i < 16; i += 2) {
+                if ((rm >> i) & 1u) r0 = fmaxf(r0, mv[i]);
+                if ((rm >> (i + 1)) & 1u) r1 = fmaxf(r1, mv[i + 1]);
+              }
+              run = fmaxf(r0, r1);
+              run = fmaxf(run, __shfl_xor_sync(0xffffffffu, run, 16));
+            } else {
+              float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
+#pragma unroll
+              for (int i = 0; i < 16; i += 4) {
+                if ((rm >> i) & 1u) r0 += mv[i];
+                if ((rm >> (i + 1)) & 1u) r1 += mv[i + 1];
+                if ((rm >> (i + 2)) & 1u) r2 += mv[i + 2];
+                if ((rm >> (i + 3)) & 1u) r3 += mv[i + 3];
+              }
+              run = (r0 + r1) + (r2 + r3);
+              const float other = __shfl_xor_sync(0xffffffffu, run, 16);
+              run = (lane < 16) ? run + other : other + run;   // rows 0-15 first, then 16-31: same order on both
+            }
+            if (lane < 16) {
+              const int node = s_row[q * 32 + end];
+              P.partials[(pair_base + (size_t)(node - first_node)) * H + c0 + lane] = run;
+            }
+            start = end + 1;
+          }
         }
+        __syncwarp();
+        SUBPH(12);                          // segment reduce
       }
       if (!P.write_e) {   // MIS last layer: edge stream is dead (gnn_encoder.py:412)
         tmem_wait_ld();
@@ -474,6 +629,7 @@ k_edge_layer_tc(const __grid_constant__ CUtensorMap wmap, const TcParams P) {
       tmem_wait_st();
       float mean1, rstd1;
       if constexpr (WPQ == 1) {
+        worker_bar();   // every warp is done with its gather buffers (stage-A memory) before E3 refills stage A
         mean1 = K1 + S1 * (1.0f / H);
         const float var1 = fmaxf(Q1 * (1.0f / H) - (S1 * (1.0f / H)) * (S1 * (1.0f / H)), 0.0f);
         rstd1 = rsqrtf(var1 + LN_EPS);
@@ -542,10 +698,12 @@ k_edge_layer_tc(const __grid_constant__ CUtensorMap wmap, const TcParams P) {
       PHASE(3);   // E2
       // ---------------- E3: s = silu(LN_O(e_til)) -> GEMM2 A operand chunks (this part's K-chunks) ----------------
 #pragma unroll 1
-      for (int kc = part * (4 / WPQ); kc < (part + 1) * (4 / WPQ); ++kc) {
-        const uint32_t u = u_tile + 4 + kc;
+      for (int idx = 0; idx < 4 / WPQ; ++idx) {
+        const int pos = part + idx * WPQ;                  // position in GEMM2's consumption order 0,2,1,3
+        const int kc = (pos & 1) * 2 + (pos >> 1);         // K-chunk (64 columns of s) at that position
+        const uint32_t u = u_tile + 4 + pos;
         const int s = u & 1, k = u >> 1;
-        unsigned char* a_hi = smem + s * TC_STAGE_BYTES;
+        unsigned char* a_hi = smem + tc_off_a(s);
         unsigned char* a_lo = a_hi + TC_A_BYTES;
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {
@@ -586,35 +744,56 @@ k_edge_layer_tc(const __grid_constant__ CUtensorMap wmap, const TcParams P) {
       mbar_wait(&acc_rdy[1], tile_par, P.error_flag, 7);
       tc_fence_after();
       PHASE(5);   // wait for GEMM2
-#pragma unroll 1
-      for (int c0 = cbase; c0 < cbase + Cfg::CPP; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(t_acc2 + c0, v);
-        tmem_wait_ld();
-        if (valid && !(P.probe & 16)) {
-          const float4* pin = reinterpret_cast<const float4*>(src + c0);
-          float4* pout = reinterpret_cast<float4*>(P.e + (size_t)s_edge * H + c0);
-          float4 ein[8];
+      {
+        // All MMAs of the tile are complete: the operand area is idle.  The fp32 residual tile comes in by
+        // TMA (8 boxes of [128 rows x 32 cols], 128B swizzle -> conflict-free thread==row access), the result
+        // is written over it and leaves by TMA store: no uncoalesced global access, e read from L2 once more.
+        const bool tma_in = !P.e_zero && !P.xt_lut;
+        if (tma_in) {
+          if (wt == 0) {
+            mbar_arrive_expect_tx(ein_bar, 8 * TC_BOX_BYTES);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) ein[j] = __ldcg(pin + j);    // 8 independent loads in flight
+            for (int j = 0; j < 8; ++j) tma_load_2d(smem_base + j * TC_BOX_BYTES, &emap, ein_bar, 32 * j, tile * TC_TILE);
+          }
+          mbar_wait(ein_bar, tile_par, P.error_flag, 10);
+        }
+#pragma unroll 1
+        for (int c0 = cbase; c0 < cbase + Cfg::CPP; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(t_acc2 + c0, v);
+          tmem_wait_ld();
+          unsigned char* box = smem + (c0 >> 5) * TC_BOX_BYTES;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
+            float4* slot = reinterpret_cast<float4*>(box + sw128_off(r, j));
+            const float4 ein = tma_in ? *slot : __ldg(reinterpret_cast<const float4*>(src + c0) + j);
             const float4 bo = *reinterpret_cast<const float4*>(prm + 5 * H + c0 + 4 * j);
             float4 o;
-            o.x = ein[j].x + __uint_as_float(v[4 * j]) + bo.x;
-            o.y = ein[j].y + __uint_as_float(v[4 * j + 1]) + bo.y;
-            o.z = ein[j].z + __uint_as_float(v[4 * j + 2]) + bo.z;
-            o.w = ein[j].w + __uint_as_float(v[4 * j + 3]) + bo.w;
-            __stcg(pout + j, o);
+            o.x = ein.x + __uint_as_float(v[4 * j]) + bo.x;
+            o.y = ein.y + __uint_as_float(v[4 * j + 1]) + bo.y;
+            o.z = ein.z + __uint_as_float(v[4 * j + 2]) + bo.z;
+            o.w = ein.w + __uint_as_float(v[4 * j + 3]) + bo.w;
+            *slot = o;
           }
+        }
+        fence_proxy_async();   // generic-proxy smem writes -> visible to the TMA store
+        tc_fence_before();
+        worker_bar();
+        if (wt == 0) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) tma_store_2d(&emap, smem_base + j * TC_BOX_BYTES, 32 * j, tile * TC_TILE);
+          tma_store_commit();
+          tma_store_wait_read();
+          mbar_arrive(e4_done);
         }
       }
       tc_fence_before();
       PHASE(6);   // E4
     }
     if (prof)
-      for (int i = 0; i < 7; ++i) atomicAdd(P.phase_cycles + i, (unsigned long long)pc[i]);
+      for (int i = 0; i < 16; ++i) atomicAdd(P.phase_cycles + i, (unsigned long long)pc[i]);
 #undef PHASE
+#undef SUBPH
   }
 
   // teardown
@@ -633,11 +812,19 @@ struct TcState {
   std::string err;
   int num_sms = 0;
   CUtensorMap wmap;
+  CUtensorMap emap;                 // fp32 edge stream [E_pad][256], box 32 cols x 128 rows, 128B swizzle
+  const void* emap_ptr = nullptr;
+  long long emap_rows = 0;
+  void* encode_fn = nullptr;
   bool bound = false;
   int last_launches = 0;
   float* zero_row = nullptr;
   int* error_flag = nullptr;
   float* debug_acc = nullptr;   // set by the debug entry point for one launch
+  const float* lin_in = nullptr;   // linear mode arguments, set for one launch by tc_launch_linear
+  float* lin_out = nullptr;
+  const float* lin_bias = nullptr;
+  int lin_rows = 0;
   int wpq = 2;                  // worker warps per TMEM lane quarter (DFB_TC_WPQ, tuning knob)
   unsigned long long* phase_cycles = nullptr;
 };
@@ -651,8 +838,6 @@ inline int tc_init(TcState* st, int num_sms) {
   cudaError_t e = cudaFuncSetAttribute(k_edge_layer_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<1>::SMEM_ALLOC);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(k_edge_layer_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<2>::SMEM_ALLOC);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(k_edge_layer_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<4>::SMEM_ALLOC);
   if (e != cudaSuccess) {
     st->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e);
     return -2;
@@ -660,12 +845,12 @@ inline int tc_init(TcState* st, int num_sms) {
   {
     const char* w = getenv("DFB_TC_WPQ");
     st->wpq = w ? atoi(w) : 2;
-    if (st->wpq != 1 && st->wpq != 2 && st->wpq != 4) st->wpq = 2;
+    if (st->wpq != 1 && st->wpq != 2) st->wpq = 2;
   }
   if ((e = cudaMalloc(&st->zero_row, H * sizeof(float))) != cudaSuccess ||
       (e = cudaMemset(st->zero_row, 0, H * sizeof(float))) != cudaSuccess ||
-      (e = cudaMalloc(&st->phase_cycles, 8 * sizeof(unsigned long long))) != cudaSuccess ||
-      (e = cudaMemset(st->phase_cycles, 0, 8 * sizeof(unsigned long long))) != cudaSuccess ||
+      (e = cudaMalloc(&st->phase_cycles, 16 * sizeof(unsigned long long))) != cudaSuccess ||
+      (e = cudaMemset(st->phase_cycles, 0, 16 * sizeof(unsigned long long))) != cudaSuccess ||
       (e = cudaMalloc(&st->error_flag, sizeof(int))) != cudaSuccess ||
       (e = cudaMemset(st->error_flag, 0, sizeof(int))) != cudaSuccess) {
     st->err = std::string("tc_init alloc: ") + cudaGetErrorString(e);
@@ -682,8 +867,8 @@ inline void tc_destroy(TcState* st) {
   st->error_flag = nullptr;
 }
 
-// One tensor map over the whole bf16 weight arena: [L*4*256 rows][256 K], rows of layer l are
-// C_hi | C_lo | O_hi | O_lo (256 rows each).  Box = 64 K x 256 rows, 128-byte swizzle.
+// One tensor map over the whole bf16 weight arena: [L*12*256 rows][256 K], rows of layer l are
+// C_hi | C_lo | O_hi | O_lo | U_hi | U_lo | V_hi | V_lo | A_hi | A_lo | B_hi | B_lo (256 rows each).  Box = 64 K x 256 rows, 128-byte swizzle.
 inline int tc_bind_weights(TcState* st, const LayerParams* layers, int L) {
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
@@ -693,7 +878,7 @@ inline int tc_bind_weights(TcState* st, const LayerParams* layers, int L) {
     cudaGetLastError();
     return -2;
   }
-  cuuint64_t gdim[2] = {(cuuint64_t)H, (cuuint64_t)L * 4 * H};
+  cuuint64_t gdim[2] = {(cuuint64_t)H, (cuuint64_t)L * 12 * H};
   cuuint64_t gstride[1] = {(cuuint64_t)H * sizeof(uint16_t)};
   cuuint32_t box[2] = {(cuuint32_t)TC_KCH, 256u};
   cuuint32_t estr[2] = {1u, 1u};
@@ -704,6 +889,7 @@ inline int tc_bind_weights(TcState* st, const LayerParams* layers, int L) {
     st->err = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r);
     return -2;
   }
+  st->encode_fn = fn;
   st->bound = true;
   return 0;
 }
@@ -716,6 +902,22 @@ inline int tc_launch_edge_layer(TcState* st, int l, float* e, const float* uvab,
     st->err = "weights not bound";
     return -1;
   }
+  const long long e_rows = (long long)((g.E + TC_TILE - 1) / TC_TILE) * TC_TILE;
+  if (st->emap_ptr != (const void*)e || st->emap_rows != e_rows) {
+    cuuint64_t gdim[2] = {(cuuint64_t)H, (cuuint64_t)e_rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)H * sizeof(float)};
+    cuuint32_t box[2] = {32u, (cuuint32_t)TC_TILE};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = ((PFN_encodeTiled)st->encode_fn)(&st->emap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)e, gdim, gstride,
+                                                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      st->err = "cuTensorMapEncodeTiled(e) failed with CUresult " + std::to_string((int)r);
+      return -2;
+    }
+    st->emap_ptr = (const void*)e;
+    st->emap_rows = e_rows;
+  }
   TcParams P;
   P.e = e; P.uvab = uvab; P.partials = partials; P.g = g; P.lp = lp; P.tvec = tvec_edge;
   P.xt_lut = xt_lut; P.lut = lut; P.zero_row = st->zero_row; P.debug_acc = st->debug_acc;
@@ -723,16 +925,17 @@ inline int tc_launch_edge_layer(TcState* st, int l, float* e, const float* uvab,
   P.phase_cycles = st->phase_cycles;
   P.write_e = st->debug_acc ? 0 : write_e;
   P.e_zero = e_zero; P.agg_mode = agg_mode;
-  P.w_row_base = l * 4 * H;
-  P.n_tiles = (g.E + TC_TILE - 1) / TC_TILE;
+  P.w_row_base = l * 12 * H;
+  P.lin_in = st->lin_in; P.lin_out = st->lin_out; P.lin_bias = st->lin_bias; P.lin_rows = st->lin_rows;
+  P.n_tiles = st->lin_out ? 4 * ((st->lin_rows + TC_TILE - 1) / TC_TILE) : (g.E + TC_TILE - 1) / TC_TILE;
+  if (st->lin_out) P.write_e = 0;
   {
     const char* pe = getenv("DFB_TC_PROBE");
     P.probe = pe ? atoi(pe) : 0;
   }
   int grid = P.n_tiles < st->num_sms ? P.n_tiles : st->num_sms;
-  if (st->wpq == 1) k_edge_layer_tc<1><<<grid, TcCfg<1>::THREADS, TcCfg<1>::SMEM_ALLOC, stream>>>(st->wmap, P);
-  else if (st->wpq == 2) k_edge_layer_tc<2><<<grid, TcCfg<2>::THREADS, TcCfg<2>::SMEM_ALLOC, stream>>>(st->wmap, P);
-  else k_edge_layer_tc<4><<<grid, TcCfg<4>::THREADS, TcCfg<4>::SMEM_ALLOC, stream>>>(st->wmap, P);
+  if (st->wpq == 1) k_edge_layer_tc<1><<<grid, TcCfg<1>::THREADS, TcCfg<1>::SMEM_ALLOC, stream>>>(st->wmap, st->emap, P);
+  else k_edge_layer_tc<2><<<grid, TcCfg<2>::THREADS, TcCfg<2>::SMEM_ALLOC, stream>>>(st->wmap, st->emap, P);
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) {
     st->err = std::string("launch: ") + cudaGetErrorString(err);
@@ -740,6 +943,16 @@ inline int tc_launch_edge_layer(TcState* st, int l, float* e, const float* uvab,
   }
   st->last_launches = 1;
   return 0;
+}
+
+// Node-side linears [rows][256] -> [rows][1024] = U|V|A|B of layer l, on the tensor-core path.
+inline int tc_launch_linear(TcState* st, int l, const float* in, float* out, const float* bias, int rows,
+                            GraphDev g, LayerParams lp, cudaStream_t stream) {
+  st->lin_in = in; st->lin_out = out; st->lin_bias = bias; st->lin_rows = rows;
+  int r = tc_launch_edge_layer(st, l, const_cast<float*>(in), nullptr, nullptr, g, lp, nullptr, 0, 0, nullptr, nullptr,
+                               AGG_SUM, stream);
+  st->lin_in = nullptr; st->lin_out = nullptr; st->lin_bias = nullptr; st->lin_rows = 0;
+  return r;
 }
 
 }  // namespace dfb

@@ -227,21 +227,26 @@ __global__ void __launch_bounds__(256) k_gn_partial(const float* __restrict__ Z,
     part[o + 1] = Q;
   }
 }
-__global__ void k_gn_final(const double* __restrict__ part, int blocks_per_seg, int rows_per_seg,
-                           float* __restrict__ stats /* [segs][32][2] mean, rstd */) {
-  int seg = blockIdx.x, gidx = threadIdx.x;   // 32 threads
+__global__ void __launch_bounds__(1024) k_gn_final(const double* __restrict__ part, int blocks_per_seg, int rows_per_seg,
+                                                   float* __restrict__ stats /* [segs][32][2] mean, rstd */) {
+  // one warp per group; lanes stride over the per-block partials, then a fixed-shape fp64 tree: deterministic
+  int seg = blockIdx.x, gidx = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double S = 0.0, Q = 0.0;
-  for (int b = 0; b < blocks_per_seg; ++b) {
+  for (int b = lane; b < blocks_per_seg; b += 32) {
     size_t o = (((size_t)seg * blocks_per_seg + b) * 32 + gidx) * 2;
     S += part[o];
     Q += part[o + 1];
   }
-  double n = (double)rows_per_seg * 8.0;
-  double mean = S / n;
-  double var = Q / n - mean * mean;
-  if (var < 0.0) var = 0.0;
-  stats[(seg * 32 + gidx) * 2] = (float)mean;
-  stats[(seg * 32 + gidx) * 2 + 1] = (float)(1.0 / sqrt(var + (double)LN_EPS));
+  S = warp_sum_d(S);
+  Q = warp_sum_d(Q);
+  if (lane == 0) {
+    double n = (double)rows_per_seg * 8.0;
+    double mean = S / n;
+    double var = Q / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stats[(seg * 32 + gidx) * 2] = (float)mean;
+    stats[(seg * 32 + gidx) * 2 + 1] = (float)(1.0 / sqrt(var + (double)LN_EPS));
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -268,30 +273,7 @@ struct PosteriorArgs {
   float* p_out;        // optional
   float* net_out;      // optional (N,out)
 };
-__global__ void __launch_bounds__(256) k_head(const float* __restrict__ Z, int R, int rows_per_seg,
-                                              const float* __restrict__ stats,
-                                              const int* __restrict__ perm, HeadParams hp,
-                                              PosteriorArgs pa) {
-  int lane = threadIdx.x & 31;
-  int r = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (r >= R) return;
-  int seg = r / rows_per_seg;
-  float mean = stats[(seg * 32 + lane) * 2], rstd = stats[(seg * 32 + lane) * 2 + 1];
-  const float4* zp = reinterpret_cast<const float4*>(Z + (size_t)r * H) + lane * 2;
-  float4 a = zp[0], b = zp[1];
-  float z[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-  float l0 = 0.f, l1 = 0.f;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    int c = lane * 8 + j;
-    float y = fmaxf(fmaf((z[j] - mean) * rstd, hp.gn_g[c], hp.gn_b[c]), 0.0f);
-    l0 = fmaf(y, hp.W[c], l0);
-    if (hp.out_channels == 2) l1 = fmaf(y, hp.W[H + c], l1);
-  }
-  l0 = warp_sum(l0) + hp.b[0];
-  if (hp.out_channels == 2) l1 = warp_sum(l1) + hp.b[1];
-  if (lane != 0) return;
-  size_t o = perm ? (size_t)perm[r] : (size_t)r;
+__device__ __forceinline__ void head_posterior(const HeadParams& hp, const PosteriorArgs& pa, size_t o, float l0, float l1) {
   if (pa.net_out) {
     pa.net_out[o * hp.out_channels] = l0;
     if (hp.out_channels == 2) pa.net_out[o * 2 + 1] = l1;
@@ -322,6 +304,69 @@ __global__ void __launch_bounds__(256) k_head(const float* __restrict__ Z, int R
     }
     pa.xt_out[o] = y;
   }
+}
+
+// A warp takes 32 consecutive rows: lane == GroupNorm group (8 channels) for the per-row partial dot products,
+// then a butterfly transpose-reduce (31 shuffles per output channel for all 32 rows) leaves row j's logits in
+// lane j, so the softmax / posterior / Philox epilogue runs on all 32 lanes in parallel.
+__global__ void __launch_bounds__(256, 2) k_head(const float* __restrict__ Z, int R, int rows_per_seg,
+                                              const float* __restrict__ stats,
+                                              const int* __restrict__ perm, HeadParams hp,
+                                              PosteriorArgs pa) {
+  const int lane = threadIdx.x & 31;
+  const int warp_global = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int r0 = warp_global * 32;
+  if (r0 >= R) return;
+  float g[8], b[8], w0[8], w1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = lane * 8 + j;
+    g[j] = hp.gn_g[c];
+    b[j] = hp.gn_b[c];
+    w0[j] = hp.W[c];
+    w1[j] = (hp.out_channels == 2) ? hp.W[H + c] : 0.0f;
+  }
+  float a0[32], a1[32];
+  int seg_prev = -1;
+  float mean = 0.f, rstd = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int r = min(r0 + i, R - 1);
+    const int seg = r / rows_per_seg;
+    if (seg != seg_prev) {   // warp-uniform
+      mean = stats[(seg * 32 + lane) * 2];
+      rstd = stats[(seg * 32 + lane) * 2 + 1];
+      seg_prev = seg;
+    }
+    const float4* zp = reinterpret_cast<const float4*>(Z + (size_t)r * H) + lane * 2;
+    const float4 x0 = __ldcs(zp), x1 = __ldcs(zp + 1);
+    const float z[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+    float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float y = fmaxf(fmaf((z[j] - mean) * rstd, g[j], b[j]), 0.0f);
+      l0 = fmaf(y, w0[j], l0);
+      l1 = fmaf(y, w1[j], l1);
+    }
+    a0[i] = l0;
+    a1[i] = l1;
+  }
+  // transpose-reduce: after the 5 stages lane L holds the full sums of row r0 + L
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float s0 = up ? a0[i] : a0[i + off], k0 = up ? a0[i + off] : a0[i];
+      const float s1 = up ? a1[i] : a1[i + off], k1 = up ? a1[i + off] : a1[i];
+      a0[i] = k0 + __shfl_xor_sync(0xffffffffu, s0, off);
+      a1[i] = k1 + __shfl_xor_sync(0xffffffffu, s1, off);
+    }
+  }
+  const int r = r0 + lane;
+  if (r >= R) return;
+  const size_t o = perm ? (size_t)perm[r] : (size_t)r;
+  head_posterior(hp, pa, o, a0[0] + hp.b[0], (hp.out_channels == 2) ? a1[0] + hp.b[1] : 0.0f);
 }
 
 }  // namespace dfb

@@ -1,0 +1,9 @@
+#!/bin/bash
+mkdir -p gpurun_out; rm -f gpurun_out/probe5.log
+for W in 2 1; do
+  echo "=== WPQ=$W parity subset ==="
+  DFB_TC_WPQ=$W timeout 600 python -m pytest tests/test_gpu_parity.py -q -m gpu -x -k "tc_gemm or (tc and (forward_tsp_categorical_golden or forward_tsp_gaussian_golden or traj_tsp_cat or traj_mis_cat or forward_mis_golden or forward_tsp_vs_oracle or forward_dense))" 2>&1 | tail -12 | tee gpurun_out/t5_w$W.log
+  for p in 128 144; do
+    DFB_TC_WPQ=$W DFB_TC_PROBE=$p timeout 300 python scripts/probe_tc.py fwd 2>&1 | grep -E "probe=" | sed "s/^/WPQ=$W /" | tee -a gpurun_out/probe5.log
+  done
+done

@@ -37,6 +37,8 @@ def t_forward(tag):
     names = ["conv", "waitG1", "E1", "E2", "E3", "waitG2", "E4"]
     print(f"{tag}: cycles/tile " + " ".join(f"{n}={c / ntile_cta:.0f}" for n, c in zip(names, pc)) +
           f" total={sum(pc[:7]) / ntile_cta:.0f}", flush=True)
+    sub = ["tmemwait", "gatherwait", "math", "gissue", "reduce"]
+    print(f"{tag}: E1 sub-phases cycles/tile " + " ".join(f"{n}={c / ntile_cta:.0f}" for n, c in zip(sub, pc[8:13])), flush=True)
 
 
 def t_gemm(tag):
