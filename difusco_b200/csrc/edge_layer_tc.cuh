@@ -195,6 +195,12 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sr
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void tmem_ldN(uint32_t taddr, uint32_t (&v)[N]);
+template <> __device__ __forceinline__ void tmem_ldN<16>(uint32_t taddr, uint32_t (&v)[16]) { tmem_ld16(taddr, v); }
+template <> __device__ __forceinline__ void tmem_ldN<32>(uint32_t taddr, uint32_t (&v)[32]) { tmem_ld32(taddr, v); }
+template <int N> __device__ __forceinline__ void tmem_stN(uint32_t taddr, const uint32_t (&v)[N]);
+template <> __device__ __forceinline__ void tmem_stN<16>(uint32_t taddr, const uint32_t (&v)[16]) { tmem_st16(taddr, v); }
+template <> __device__ __forceinline__ void tmem_stN<32>(uint32_t taddr, const uint32_t (&v)[32]) { tmem_st32(taddr, v); }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
@@ -204,6 +210,37 @@ __device__ __forceinline__ float sigmoid_mufu(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(-1.4426950408889634f * x));
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + t));
   return r;
+}
+// Packed fp32x2 arithmetic (Blackwell FADD2 / FMUL2 / FFMA2): two independent IEEE fp32 operations per instruction
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  float2 d;
+  asm("{.reg .b64 ra, rb, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; add.rn.f32x2 rd, ra, rb; mov.b64 {%0,%1}, rd;}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  float2 d;
+  asm("{.reg .b64 ra, rb, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mul.rn.f32x2 rd, ra, rb; mov.b64 {%0,%1}, rd;}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{.reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mov.b64 rc, {%6,%7}; "
+      "fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0,%1}, rd;}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ float2 splat2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 sigmoid_mufu2(float2 x) {
+  const float2 t = mul2(x, splat2(-1.4426950408889634f));
+  float e0, e1, r0, r1;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(t.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(t.y));
+  const float2 y = add2(make_float2(e0, e1), splat2(1.0f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(y.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(y.y));
+  return make_float2(r0, r1);
 }
 // fp32 x4 -> bf16 hi x4, bf16 lo x4 (lo = rn(x - hi))
 __device__ __forceinline__ void split4(float4 x, uint2& hi, uint2& lo) {
@@ -227,34 +264,32 @@ __device__ __forceinline__ uint32_t sw128_off(int r, int j) {
 // LayerNorm partial statistics of the slices are combined through shared memory.
 template <int WPQ>
 struct TcCfg {
-  static_assert(WPQ == 1 || WPQ == 2, "1 or 2 worker warps per TMEM lane quarter");
+  static_assert(WPQ == 1 || WPQ == 2 || WPQ == 4, "1, 2 or 4 worker warps per TMEM lane quarter");
   static constexpr int NWORK = 128 * WPQ;                 // worker threads
   static constexpr int THREADS = 64 + NWORK;
   static constexpr int CPP = H / WPQ;                     // columns per part
-  static constexpr int PATCH_COLS = 16;                   // E1 works in 16-column sub-chunks
-  static constexpr int OFF_PATCH = TC_OFF_PRM + 6 * H * 4;
-  static constexpr int OFF_STAT1 = OFF_PATCH + 4 * WPQ * PATCH_COLS * 36 * 4;
-  static constexpr int OFF_STAT2 = OFF_STAT1 + WPQ * TC_TILE * 16;
-  static constexpr int OFF_ROW = OFF_STAT2 + WPQ * TC_TILE * 8;
+  static constexpr int PATCH_COLS = (WPQ == 4) ? 8 : 16;  // columns per segment-reduce pass (E1 sub-chunk = 16 columns)
+  static constexpr int CW = (WPQ == 4) ? 16 : 32;         // TMEM chunk width of E2/E3/E4 (register budget)
+  static constexpr bool PREFETCH = (WPQ != 4);            // register prefetch of the next sub-chunk (register budget)
+  static constexpr bool GATE_B0 = (WPQ == 4);             // gather buffers spill into B0: GEMM2's first weights wait for E1
+  static constexpr int OFF_PATCH = TC_OFF_PRM + 6 * H * 4;   // per warp PATCH_COLS x 36 floats; also carries the LN statistics
+  static constexpr int OFF_ROW = OFF_PATCH + 4 * WPQ * PATCH_COLS * 36 * 4;
   static constexpr int OFF_COL = OFF_ROW + TC_TILE * 4;
   static constexpr int OFF_SRC = OFF_COL + TC_TILE * 4;
   static constexpr int OFF_BAR = OFF_SRC + TC_TILE * 8;
   static constexpr int SMEM_BYTES = OFF_BAR + 128;
   static constexpr int SMEM_ALLOC = SMEM_BYTES + 1024;    // slack for 1024-byte alignment
   static_assert(SMEM_ALLOC <= 232448, "shared memory budget");
+  static_assert(PATCH_COLS * 36 >= 192, "patch must hold the per-warp LayerNorm statistics");
 };
 
 template <int WPQ>
-__global__ void __launch_bounds__(TcCfg<WPQ>::THREADS, 1)
-k_edge_layer_tc(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap emap,
-                const TcParams P) {
+__device__ __forceinline__ void edge_layer_tc_body(const CUtensorMap& wmap, const CUtensorMap& emap, const TcParams& P) {
   using Cfg = TcCfg<WPQ>;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays in .shared
   float* prm = reinterpret_cast<float*>(smem + TC_OFF_PRM);      // ln_e_g, ln_e_b, tau, ln_o_g, ln_o_b, b_O
   float* patch_all = reinterpret_cast<float*>(smem + Cfg::OFF_PATCH);
-  float4* stat1 = reinterpret_cast<float4*>(smem + Cfg::OFF_STAT1);   // [WPQ][128] (K, S, Q, -)
-  float2* stat2 = reinterpret_cast<float2*>(smem + Cfg::OFF_STAT2);   // [WPQ][128] (S, Q)
   int* s_row = reinterpret_cast<int*>(smem + Cfg::OFF_ROW);
   int* s_col = reinterpret_cast<int*>(smem + Cfg::OFF_COL);
   const float** s_src = reinterpret_cast<const float**>(smem + Cfg::OFF_SRC);
@@ -266,7 +301,8 @@ k_edge_layer_tc(const __grid_constant__ CUtensorMap wmap, const __grid_constant_
   uint64_t* acc_rdy = bars + 8;   // [2] MMA commit -> workers (GEMM1 / GEMM2 accumulator complete)
   uint64_t* ein_bar = bars + 10;  // TMA load of the residual tile (expect_tx)
   uint64_t* e4_done = bars + 11;  // staging (A0|A1|B0) released after the TMA store has read it
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* e1_done = bars + 12;  // all warps left E1: the B0 region no longer holds gather buffers (GATE_B0)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int uses_per_tile = P.write_e ? 8 : 4;
@@ -278,6 +314,7 @@ k_edge_layer_tc(const __grid_constant__ CUtensorMap wmap, const __grid_constant_
     mbar_init(&empty[0], 1);            mbar_init(&empty[1], 1);
     mbar_init(&acc_rdy[0], 1);          mbar_init(&acc_rdy[1], 1);
     mbar_init(ein_bar, 1);              mbar_init(e4_done, 1);
+    mbar_init(e1_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_proxy_async();
   }
@@ -315,13 +352,17 @@ k_edge_layer_tc(const __grid_constant__ CUtensorMap wmap, const __grid_constant_
         for (int i = 0; i < uses_per_tile; ++i, ++u) {
           const int s = u & 1, k = u >> 1, kc = i & 3;
           mbar_wait(&empty[s], (k & 1) ^ 1, P.error_flag, 1);
+          if (Cfg::GATE_B0 && i == 4) mbar_wait(e1_done, tile_it & 1, P.error_flag, 11);
+          // without GEMM2 (MIS last layer) the next fill of B0 is the NEXT tile's first chunk: same gate, previous tile
+          if (Cfg::GATE_B0 && i == 0 && tile_it > 0 && !P.write_e && !P.lin_out && !P.debug_acc)
+            mbar_wait(e1_done, (tile_it - 1) & 1, P.error_flag, 12);
           mbar_arrive_expect_tx(&full_b[s], 2 * TC_B_BYTES);
           const uint32_t dst = smem_base + tc_off_b(s);
           // C_hi,C_lo | O_hi,O_lo blocks of 256 rows; linear mode: U|V|A|B (hi,lo) blocks follow at +1024
           const int rb = P.lin_out ? P.w_row_base + 1024 + (tile & 3) * 512 : P.w_row_base + (i < 4 ? 0 : 512);
           // GEMM2 consumes its K-chunks in the order 0,2,1,3 so that with two column parts (chunks {0,1} and {2,3})
           // both parts' first chunks feed the tensor core while E3 is still producing the second ones
-          const int kw = (i >= 4 && !P.lin_out) ? ((kc & 1) * 2 + (kc >> 1)) : kc;
+          const int kw = (WPQ != 4 && i >= 4 && !P.lin_out) ? ((kc & 1) * 2 + (kc >> 1)) : kc;
           tma_load_2d(dst, &wmap, &full_b[s], kw * TC_KCH, rb);
           tma_load_2d(dst + TC_B_BYTES, &wmap, &full_b[s], kw * TC_KCH, rb + 256);
         }
@@ -365,13 +406,22 @@ k_edge_layer_tc(const __grid_constant__ CUtensorMap wmap, const __grid_constant_
     const uint32_t t_acc1 = tmem_base + ((uint32_t)(q * 32) << 16);
     const uint32_t t_acc2 = t_acc1 + 256u;
     auto worker_bar = [] { asm volatile("bar.sync 1, %0;" ::"n"(Cfg::NWORK) : "memory"); };
+#ifdef DFB_PHASE_PROF   // tuning build only (python -m difusco_b200.build --prof): per-phase clock64 counters of worker thread 0
     const bool prof = (P.probe & 128) && wt == 0;
     long long pc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tp = 0, tq = 0;
-#define SUBPH(i) do { if (prof) { long long _n = clock64(); pc[i] += _n - tq; tq = _n; } } while (0)
 #define PHASE(i) do { if (prof) { long long _n = clock64(); pc[i] += _n - tp; tp = _n; } } while (0)
+#define SUBPH(i) do { if (prof) { long long _n = clock64(); pc[i] += _n - tq; tq = _n; } } while (0)
+#define PROF_TILE_START() do { if (prof) tp = clock64(); } while (0)
+#define PROF_SUB_START() do { if (prof) tq = clock64(); } while (0)
+#else
+#define PHASE(i) do { } while (0)
+#define SUBPH(i) do { } while (0)
+#define PROF_TILE_START() do { } while (0)
+#define PROF_SUB_START() do { } while (0)
+#endif
     uint32_t u_tile = 0;
     for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, u_tile += uses_per_tile) {
-      if (prof) tp = clock64();
+      PROF_TILE_START();
       const int s_edge = (P.lin_out ? (tile >> 2) : tile) * TC_TILE + r;
       const bool valid = s_edge < (P.lin_out ? P.lin_rows : P.g.E);
       int my_row = -1, my_col = 0;
@@ -492,7 +542,7 @@ k_edge_layer_tc(const __grid_constant__ CUtensorMap wmap, const __grid_constant_
       // Every warp stages only its own 32 rows (two 4 KB buffers: sub-chunk i+1 in flight while i is consumed),
       // so __syncwarp is the only synchronisation.  TMEM data and the B h[row] values of the next sub-chunk are
       // prefetched into registers.
-      unsigned char* gbuf0 = smem + tc_off_a(part) + q * 8192;
+      unsigned char* gbuf0 = smem + (warp - 2) * 8192;   // WPQ 1,2: inside A0|A1; WPQ 4: A0|A1|B0 (GATE_B0)
       unsigned char* gbuf1 = gbuf0 + 4096;
       // lane handles piece (lane & 7) of rows (it*4 + lane/8): source pointers / smem offsets are fixed per tile
       const float* gptr[8];
@@ -515,221 +565,264 @@ k_edge_layer_tc(const __grid_constant__ CUtensorMap wmap, const __grid_constant_
       const float4* pb = reinterpret_cast<const float4*>(uv_row + 3 * H + cbase);
       uint32_t vn[16];
       float4 bn[4];
-      tmem_ld16(t_acc1 + cbase, vn);
+      if constexpr (Cfg::PREFETCH) {
+        tmem_ld16(t_acc1 + cbase, vn);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) bn[j] = __ldg(pb + j);
-      float K1 = 0.f, S1 = 0.f, Q1 = 0.f;
+        for (int j = 0; j < 4; ++j) bn[j] = __ldg(pb + j);
+      }
+      float2 nK = splat2(0.f), S1p = splat2(0.f), S1q = splat2(0.f), Q1p = splat2(0.f), Q1q = splat2(0.f);
+      constexpr int PC = Cfg::PATCH_COLS;
 #pragma unroll 1
       for (int sub = 0; sub < NSUB; ++sub) {
         const int c0 = cbase + sub * 16;
         unsigned char* buf = (sub & 1) ? gbuf1 : gbuf0;
         uint32_t v[16];
         float4 bb[4];
-        if (prof) tq = clock64();
-        tmem_wait_ld();
+        PROF_SUB_START();
+        if constexpr (Cfg::PREFETCH) {
+          tmem_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = vn[j];
+          for (int j = 0; j < 16; ++j) v[j] = vn[j];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) bb[j] = bn[j];
-        if (sub + 1 < NSUB) {               // prefetch the next sub-chunk
-          tmem_ld16(t_acc1 + c0 + 16, vn);
+          for (int j = 0; j < 4; ++j) bb[j] = bn[j];
+          if (sub + 1 < NSUB) {               // prefetch the next sub-chunk
+            tmem_ld16(t_acc1 + c0 + 16, vn);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) bn[j] = __ldg(pb + 4 * (sub + 1) + j);
+            for (int j = 0; j < 4; ++j) bn[j] = __ldg(pb + 4 * (sub + 1) + j);
+          }
+        } else {
+          tmem_ld16(t_acc1 + c0, v);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) bb[j] = __ldg(pb + 4 * sub + j);
+          tmem_wait_ld();
         }
         SUBPH(8);                           // tmem wait + prefetch issue
         if (sub + 1 < NSUB) cp_async_wait<1>(); else cp_async_wait<0>();
         __syncwarp();                       // this warp's pieces of the sub-chunk have landed
         SUBPH(9);                           // gather wait
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float4 a, vv;
-          if (P.probe & 1) { a = vv = make_float4(0.1f, 0.2f, 0.3f, 0.4f); }
-          else {
-            a = *reinterpret_cast<const float4*>(buf + sw128_off(lane, j));
-            vv = *reinterpret_cast<const float4*>(buf + sw128_off(lane, 4 + j));
-          }
-          const float4 b = bb[j];
-          float xs[4] = {__uint_as_float(v[4 * j]) + a.x + b.x, __uint_as_float(v[4 * j + 1]) + a.y + b.y,
-                         __uint_as_float(v[4 * j + 2]) + a.z + b.z, __uint_as_float(v[4 * j + 3]) + a.w + b.w};
-          const float vs[4] = {vv.x, vv.y, vv.z, vv.w};
-          if (sub == 0 && j == 0) K1 = xs[0];
+        for (int ps = 0; ps < 16 / PC; ++ps) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float d = xs[i] - K1;
-            S1 += d;
-            Q1 = fmaf(d, d, Q1);
-            float m = sigmoid_mufu(xs[i]) * vs[i];
-            if (!valid) m = (P.agg_mode == AGG_MAX) ? -INFINITY : 0.0f;
-            patch[(4 * j + i) * 36 + lane] = m;   // transposed [column][row]: conflict-free (4c + lane)
-            v[4 * j + i] = __float_as_uint(xs[i]);
+          for (int jj = 0; jj < PC / 4; ++jj) {
+            const int j = ps * (PC / 4) + jj;
+            float4 a, vv;
+            if (P.probe & 1) { a = vv = make_float4(0.1f, 0.2f, 0.3f, 0.4f); }
+            else {
+              a = *reinterpret_cast<const float4*>(buf + sw128_off(lane, j));
+              vv = *reinterpret_cast<const float4*>(buf + sw128_off(lane, 4 + j));
+            }
+            const float4 b = bb[j];
+            float2 x01 = add2(add2(make_float2(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1])),
+                                   make_float2(a.x, a.y)), make_float2(b.x, b.y));
+            float2 x23 = add2(add2(make_float2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])),
+                                   make_float2(a.z, a.w)), make_float2(b.z, b.w));
+            if (sub == 0 && j == 0) nK = splat2(-x01.x);
+            const float2 d01 = add2(x01, nK), d23 = add2(x23, nK);
+            S1p = add2(S1p, d01);
+            S1q = add2(S1q, d23);
+            Q1p = fma2(d01, d01, Q1p);
+            Q1q = fma2(d23, d23, Q1q);
+            float2 m01 = mul2(sigmoid_mufu2(x01), make_float2(vv.x, vv.y));
+            float2 m23 = mul2(sigmoid_mufu2(x23), make_float2(vv.z, vv.w));
+            if (!valid) m01 = m23 = splat2((P.agg_mode == AGG_MAX) ? -INFINITY : 0.0f);
+            patch[(4 * jj + 0) * 36 + lane] = m01.x;   // transposed [column][row]: conflict-free (4c + lane)
+            patch[(4 * jj + 1) * 36 + lane] = m01.y;
+            patch[(4 * jj + 2) * 36 + lane] = m23.x;
+            patch[(4 * jj + 3) * 36 + lane] = m23.y;
+            v[4 * j] = __float_as_uint(x01.x);
+            v[4 * j + 1] = __float_as_uint(x01.y);
+            v[4 * j + 2] = __float_as_uint(x23.x);
+            v[4 * j + 3] = __float_as_uint(x23.y);
           }
+          __syncwarp();                     // patch pass complete
+          // row-segment reduction: lane = (column = lane % PC, row group = lane / PC) sums its PC rows of every node
+          // segment from the transposed patch; row groups are combined with shuffles; seg_mask is warp-uniform;
+          // partial rows leave as coalesced stores
+          {
+            const float* pcol = patch + (lane % PC) * 36;
+            const int r_lo = (lane / PC) * PC, r_hi = r_lo + PC - 1;
+            float mv[PC];
+#pragma unroll
+            for (int j4 = 0; j4 < PC / 4; ++j4) {
+              const float4 t4 = *reinterpret_cast<const float4*>(pcol + r_lo + 4 * j4);
+              mv[4 * j4] = t4.x; mv[4 * j4 + 1] = t4.y; mv[4 * j4 + 2] = t4.z; mv[4 * j4 + 3] = t4.w;
+            }
+            uint32_t mask = seg_mask;
+            int start = 0;
+            while (mask) {                         // one iteration per node segment present in this warp
+              const int end = __ffs(mask) - 1;
+              mask &= mask - 1;
+              const int lo = max(start, r_lo) - r_lo, hi = min(end, r_hi) - r_lo;   // my PC rows of this segment
+              const uint32_t rm = (hi >= lo) ? (((2u << hi) - 1u) & ~((1u << lo) - 1u)) : 0u;
+              float run;
+              if (P.agg_mode == AGG_MAX) {
+                float r0 = -INFINITY, r1 = -INFINITY;
+#pragma unroll
+                for (int i = 0; i < PC; i += 2) {
+                  if ((rm >> i) & 1u) r0 = fmaxf(r0, mv[i]);
+                  if ((rm >> (i + 1)) & 1u) r1 = fmaxf(r1, mv[i + 1]);
+                }
+                run = fmaxf(r0, r1);
+#pragma unroll
+                for (int off = PC; off < 32; off <<= 1) run = fmaxf(run, __shfl_xor_sync(0xffffffffu, run, off));
+              } else {
+                float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
+#pragma unroll
+                for (int i = 0; i < PC; i += 4) {
+                  if ((rm >> i) & 1u) r0 += mv[i];
+                  if ((rm >> (i + 1)) & 1u) r1 += mv[i + 1];
+                  if ((rm >> (i + 2)) & 1u) r2 += mv[i + 2];
+                  if ((rm >> (i + 3)) & 1u) r3 += mv[i + 3];
+                }
+                run = (r0 + r1) + (r2 + r3);
+#pragma unroll
+                for (int off = PC; off < 32; off <<= 1) run += __shfl_xor_sync(0xffffffffu, run, off);   // fixed tree
+              }
+              if (lane < PC) {
+                const int node = s_row[q * 32 + end];
+                P.partials[(pair_base + (size_t)(node - first_node)) * H + c0 + ps * PC + lane] = run;
+              }
+              start = end + 1;
+            }
+          }
+          __syncwarp();                     // patch may be rewritten
         }
         if (P.write_e) tmem_st16(t_acc1 + c0, v);
-        __syncwarp();                       // buffer consumed, patch complete
-        SUBPH(10);                          // math
+        SUBPH(10);                          // math + segment reduce
         if (sub + 2 < NSUB) gather_issue(sub + 2, buf);
         SUBPH(11);                          // gather issue
-        // row-segment reduction: lane = (column c = lane & 15, row half = lane >> 4) sums its 16 rows of every
-        // node segment from the transposed patch, halves are combined with one shuffle; seg_mask is
-        // warp-uniform; partial rows leave as coalesced stores
-        {
-          const float* pcol = patch + (lane & 15) * 36;
-          const int r_lo = (lane >> 4) * 16, r_hi = r_lo + 15;
-          float mv[16];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 t4 = *reinterpret_cast<const float4*>(pcol + r_lo + 4 * j);
-            mv[4 * j] = t4.x; mv[4 * j + 1] = t4.y; mv[4 * j + 2] = t4.z; mv[4 * j + 3] = t4.w;
-          }
-          uint32_t mask = seg_mask;
-          int start = 0;
-          while (mask) {                         // one iteration per node segment present in this warp
-            const int end = __ffs(mask) - 1;
-            mask &= mask - 1;
-            const int lo = max(start, r_lo) - r_lo, hi = min(end, r_hi) - r_lo;   // my 16 rows of this segment
-            const uint32_t rm = (hi >= lo) ? (((2u << hi) - 1u) & ~((1u << lo) - 1u)) : 0u;
-            float run;
-            if (P.agg_mode == AGG_MAX) {
-              float r0 = -INFINITY, r1 = -INFINITY;
-#pragma unroll
-              for (int i = 0; i < 16; i += 2) {
-                if ((rm >> i) & 1u) r0 = fmaxf(r0, mv[i]);
-                if ((rm >> (i + 1)) & 1u) r1 = fmaxf(r1, mv[i + 1]);
-              }
-              run = fmaxf(r0, r1);
-              run = fmaxf(run, __shfl_xor_sync(0xffffffffu, run, 16));
-            } else {
-              float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
-#pragma unroll
-              for (int i = 0; i < 16; i += 4) {
-                if ((rm >> i) & 1u) r0 += mv[i];
-                if ((rm >> (i + 1)) & 1u) r1 += mv[i + 1];
-                if ((rm >> (i + 2)) & 1u) r2 += mv[i + 2];
-                if ((rm >> (i + 3)) & 1u) r3 += mv[i + 3];
-              }
-              run = (r0 + r1) + (r2 + r3);
-              const float other = __shfl_xor_sync(0xffffffffu, run, 16);
-              run = (lane < 16) ? run + other : other + run;   // rows 0-15 first, then 16-31: same order on both
-            }
-            if (lane < 16) {
-              const int node = s_row[q * 32 + end];
-              P.partials[(pair_base + (size_t)(node - first_node)) * H + c0 + lane] = run;
-            }
-            start = end + 1;
-          }
-        }
-        __syncwarp();
-        SUBPH(12);                          // segment reduce
       }
+      const float K1 = -nK.x, S1 = (S1p.x + S1p.y) + (S1q.x + S1q.y), Q1 = (Q1p.x + Q1p.y) + (Q1q.x + Q1q.y);
       if (!P.write_e) {   // MIS last layer: edge stream is dead (gnn_encoder.py:412)
         tmem_wait_ld();
         tc_fence_before();
+        if constexpr (Cfg::GATE_B0) {   // gather buffers (in B0) are dead once every warp has left E1
+          worker_bar();
+          if (wt == 0) mbar_arrive(e1_done);
+        }
         continue;
       }
       tmem_wait_st();
       float mean1, rstd1;
+      // LayerNorm statistics of the column parts are exchanged through the (now idle) per-warp patches:
+      // warp (part, q) publishes its 32 rows at patch[0..95] (K,S,Q) and patch[128..191] (S2,Q2)
       if constexpr (WPQ == 1) {
         worker_bar();   // every warp is done with its gather buffers (stage-A memory) before E3 refills stage A
         mean1 = K1 + S1 * (1.0f / H);
         const float var1 = fmaxf(Q1 * (1.0f / H) - (S1 * (1.0f / H)) * (S1 * (1.0f / H)), 0.0f);
         rstd1 = rsqrtf(var1 + LN_EPS);
       } else {
-        stat1[part * TC_TILE + r] = make_float4(K1, S1, Q1, 0.f);
+        patch[lane] = K1;
+        patch[32 + lane] = S1;
+        patch[64 + lane] = Q1;
         worker_bar();
-        float4 st[WPQ];
+        if (Cfg::GATE_B0 && wt == 0) mbar_arrive(e1_done);   // gather buffers are dead: GEMM2's weights may fill B0
+        float kk[WPQ], sp[WPQ], qp[WPQ];
         float msum = 0.f;
 #pragma unroll
         for (int p2 = 0; p2 < WPQ; ++p2) {
-          st[p2] = stat1[p2 * TC_TILE + r];
-          msum += st[p2].x * (float)Cfg::CPP + st[p2].y;
+          const float* pp = patch_all + (p2 * 4 + ((warp - 2) & 3)) * Cfg::PATCH_COLS * 36;
+          kk[p2] = pp[lane]; sp[p2] = pp[32 + lane]; qp[p2] = pp[64 + lane];
+          msum += kk[p2] * (float)Cfg::CPP + sp[p2];
         }
         mean1 = msum * (1.0f / H);
         float ss = 0.f;   // sum (x - mean)^2 = sum_p [Q_p - 2 (mean - K_p) S_p + n_p (mean - K_p)^2]
 #pragma unroll
         for (int p2 = 0; p2 < WPQ; ++p2) {
-          const float dk = mean1 - st[p2].x;
-          ss += st[p2].z - 2.0f * dk * st[p2].y + (float)Cfg::CPP * dk * dk;
+          const float dk = mean1 - kk[p2];
+          ss += qp[p2] - 2.0f * dk * sp[p2] + (float)Cfg::CPP * dk * dk;
         }
         rstd1 = rsqrtf(fmaxf(ss * (1.0f / H), 0.0f) + LN_EPS);
       }
-
       PHASE(2);   // E1 (+ stats exchange)
       // ---------------- E2: e_til = relu(LN_e(e_hat)) + tau, statistics for LN_O ----------------
-      float S2 = 0.f, Q2 = 0.f;   // e_til = relu(.)+tau is O(1) with mean ~ std: plain sums are safe in fp32
+      float S2, Q2;   // e_til = relu(.)+tau is O(1) with mean ~ std: plain sums are safe in fp32
+      {
+        const float2 rs = splat2(rstd1), nm = splat2(-mean1 * rstd1);
+        float2 S2p = splat2(0.f), Q2p = splat2(0.f);
 #pragma unroll 1
-      for (int c0 = cbase; c0 < cbase + Cfg::CPP; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(t_acc1 + c0, v);
-        tmem_wait_ld();
+        for (int c0 = cbase; c0 < cbase + Cfg::CPP; c0 += Cfg::CW) {
+          uint32_t v[Cfg::CW];
+          tmem_ldN<Cfg::CW>(t_acc1 + c0, v);
+          tmem_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 g4 = *reinterpret_cast<const float4*>(prm + c0 + 4 * j);
-          const float4 b4 = *reinterpret_cast<const float4*>(prm + H + c0 + 4 * j);
-          const float4 t4 = *reinterpret_cast<const float4*>(prm + 2 * H + c0 + 4 * j);
-          const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
-          const float tt[4] = {t4.x, t4.y, t4.z, t4.w};
+          for (int j = 0; j < Cfg::CW / 4; ++j) {
+            const float4 g4 = *reinterpret_cast<const float4*>(prm + c0 + 4 * j);
+            const float4 b4 = *reinterpret_cast<const float4*>(prm + H + c0 + 4 * j);
+            const float4 t4 = *reinterpret_cast<const float4*>(prm + 2 * H + c0 + 4 * j);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float y = fmaxf(fmaf((__uint_as_float(v[4 * j + i]) - mean1) * rstd1, gg[i], bb[i]), 0.0f) + tt[i];
-            S2 += y;
-            Q2 = fmaf(y, y, Q2);
-            v[4 * j + i] = __float_as_uint(y);
+            for (int hh = 0; hh < 2; ++hh) {
+              const float2 x = make_float2(__uint_as_float(v[4 * j + 2 * hh]), __uint_as_float(v[4 * j + 2 * hh + 1]));
+              const float2 gg = hh ? make_float2(g4.z, g4.w) : make_float2(g4.x, g4.y);
+              const float2 bb2 = hh ? make_float2(b4.z, b4.w) : make_float2(b4.x, b4.y);
+              const float2 tt = hh ? make_float2(t4.z, t4.w) : make_float2(t4.x, t4.y);
+              float2 y = fma2(fma2(x, rs, nm), gg, bb2);          // LN_e affine
+              y = add2(make_float2(fmaxf(y.x, 0.0f), fmaxf(y.y, 0.0f)), tt);   // ReLU + time vector
+              S2p = add2(S2p, y);
+              Q2p = fma2(y, y, Q2p);
+              v[4 * j + 2 * hh] = __float_as_uint(y.x);
+              v[4 * j + 2 * hh + 1] = __float_as_uint(y.y);
+            }
           }
+          tmem_stN<Cfg::CW>(t_acc1 + c0, v);
         }
-        tmem_st32(t_acc1 + c0, v);
+        S2 = S2p.x + S2p.y;
+        Q2 = Q2p.x + Q2p.y;
       }
       tmem_wait_st();
       if constexpr (WPQ > 1) {
-        stat2[part * TC_TILE + r] = make_float2(S2, Q2);
+        patch[128 + lane] = S2;
+        patch[160 + lane] = Q2;
         worker_bar();
         S2 = 0.f;
         Q2 = 0.f;
 #pragma unroll
         for (int p2 = 0; p2 < WPQ; ++p2) {
-          const float2 t2 = stat2[p2 * TC_TILE + r];
-          S2 += t2.x;
-          Q2 += t2.y;
+          const float* pp = patch_all + (p2 * 4 + ((warp - 2) & 3)) * Cfg::PATCH_COLS * 36;
+          S2 += pp[128 + lane];
+          Q2 += pp[160 + lane];
         }
       }
       const float mean2 = S2 * (1.0f / H);
       const float var2 = fmaxf(Q2 * (1.0f / H) - mean2 * mean2, 0.0f);
       const float rstd2 = rsqrtf(var2 + LN_EPS);
+      const float2 rs2 = splat2(rstd2), nm2 = splat2(-mean2 * rstd2);
 
       PHASE(3);   // E2
       // ---------------- E3: s = silu(LN_O(e_til)) -> GEMM2 A operand chunks (this part's K-chunks) ----------------
 #pragma unroll 1
       for (int idx = 0; idx < 4 / WPQ; ++idx) {
         const int pos = part + idx * WPQ;                  // position in GEMM2's consumption order 0,2,1,3
-        const int kc = (pos & 1) * 2 + (pos >> 1);         // K-chunk (64 columns of s) at that position
+        const int kc = (WPQ == 4) ? pos : (pos & 1) * 2 + (pos >> 1);   // K-chunk (64 columns of s) at that position
         const uint32_t u = u_tile + 4 + pos;
         const int s = u & 1, k = u >> 1;
         unsigned char* a_hi = smem + tc_off_a(s);
         unsigned char* a_lo = a_hi + TC_A_BYTES;
 #pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
-          const int c0 = kc * TC_KCH + half * 32;
-          uint32_t v[32];
-          tmem_ld32(t_acc1 + c0, v);
+        for (int piece = 0; piece < TC_KCH / Cfg::CW; ++piece) {
+          const int c0 = kc * TC_KCH + piece * Cfg::CW;
+          uint32_t v[Cfg::CW];
+          tmem_ldN<Cfg::CW>(t_acc1 + c0, v);
           tmem_wait_ld();
-          if (half == 0) mbar_wait(&empty[s], (k & 1) ^ 1, P.error_flag, 6);
+          if (piece == 0) mbar_wait(&empty[s], (k & 1) ^ 1, P.error_flag, 6);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {   // 4 x 16-byte units of 8 bf16
+          for (int j = 0; j < Cfg::CW / 8; ++j) {   // 16-byte units of 8 bf16
             float z[8];
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
               const float4 g4 = *reinterpret_cast<const float4*>(prm + 3 * H + c0 + 8 * j + 4 * hh);
               const float4 b4 = *reinterpret_cast<const float4*>(prm + 4 * H + c0 + 8 * j + 4 * hh);
-              const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float t = fmaf((__uint_as_float(v[8 * j + 4 * hh + i]) - mean2) * rstd2, gg[i], bb[i]);
-                z[4 * hh + i] = t * sigmoid_mufu(t);
-              }
+              const float2 t01 = fma2(fma2(make_float2(__uint_as_float(v[8 * j + 4 * hh]), __uint_as_float(v[8 * j + 4 * hh + 1])),
+                                           rs2, nm2), make_float2(g4.x, g4.y), make_float2(b4.x, b4.y));
+              const float2 t23 = fma2(fma2(make_float2(__uint_as_float(v[8 * j + 4 * hh + 2]), __uint_as_float(v[8 * j + 4 * hh + 3])),
+                                           rs2, nm2), make_float2(g4.z, g4.w), make_float2(b4.z, b4.w));
+              const float2 s01 = mul2(t01, sigmoid_mufu2(t01)), s23 = mul2(t23, sigmoid_mufu2(t23));   // SiLU
+              z[4 * hh] = s01.x; z[4 * hh + 1] = s01.y; z[4 * hh + 2] = s23.x; z[4 * hh + 3] = s23.y;
             }
             uint2 h0, l0, h1, l1;
             split4(make_float4(z[0], z[1], z[2], z[3]), h0, l0);
             split4(make_float4(z[4], z[5], z[6], z[7]), h1, l1);
-            const uint32_t off = sw128_off(r, half * 4 + j);
+            const uint32_t off = sw128_off(r, piece * (Cfg::CW / 8) + j);
             *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(h0.x, h0.y, h1.x, h1.y);
             *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(l0.x, l0.y, l1.x, l1.y);
           }
@@ -758,21 +851,22 @@ k_edge_layer_tc(const __grid_constant__ CUtensorMap wmap, const __grid_constant_
           mbar_wait(ein_bar, tile_par, P.error_flag, 10);
         }
 #pragma unroll 1
-        for (int c0 = cbase; c0 < cbase + Cfg::CPP; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld32(t_acc2 + c0, v);
+        for (int c0 = cbase; c0 < cbase + Cfg::CPP; c0 += Cfg::CW) {
+          uint32_t v[Cfg::CW];
+          tmem_ldN<Cfg::CW>(t_acc2 + c0, v);
           tmem_wait_ld();
           unsigned char* box = smem + (c0 >> 5) * TC_BOX_BYTES;
+          const int u0 = (c0 & 31) >> 2;   // first 16-byte unit of this chunk inside its 32-column box
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4* slot = reinterpret_cast<float4*>(box + sw128_off(r, j));
+          for (int j = 0; j < Cfg::CW / 4; ++j) {
+            float4* slot = reinterpret_cast<float4*>(box + sw128_off(r, u0 + j));
             const float4 ein = tma_in ? *slot : __ldg(reinterpret_cast<const float4*>(src + c0) + j);
             const float4 bo = *reinterpret_cast<const float4*>(prm + 5 * H + c0 + 4 * j);
-            float4 o;
-            o.x = ein.x + __uint_as_float(v[4 * j]) + bo.x;
-            o.y = ein.y + __uint_as_float(v[4 * j + 1]) + bo.y;
-            o.z = ein.z + __uint_as_float(v[4 * j + 2]) + bo.z;
-            o.w = ein.w + __uint_as_float(v[4 * j + 3]) + bo.w;
+            const float2 o01 = add2(add2(make_float2(ein.x, ein.y), make_float2(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]))),
+                                    make_float2(bo.x, bo.y));
+            const float2 o23 = add2(add2(make_float2(ein.z, ein.w), make_float2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]))),
+                                    make_float2(bo.z, bo.w));
+            const float4 o = make_float4(o01.x, o01.y, o23.x, o23.y);
             *slot = o;
           }
         }
@@ -790,10 +884,14 @@ k_edge_layer_tc(const __grid_constant__ CUtensorMap wmap, const __grid_constant_
       tc_fence_before();
       PHASE(6);   // E4
     }
+#ifdef DFB_PHASE_PROF
     if (prof)
       for (int i = 0; i < 16; ++i) atomicAdd(P.phase_cycles + i, (unsigned long long)pc[i]);
+#endif
 #undef PHASE
 #undef SUBPH
+#undef PROF_TILE_START
+#undef PROF_SUB_START
   }
 
   // teardown
@@ -803,6 +901,17 @@ k_edge_layer_tc(const __grid_constant__ CUtensorMap wmap, const __grid_constant_
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
+}
+
+// Kernel entry points: one per worker-warp count.  (576 threads are allocated as 20 warps: 96 registers per thread.)
+template <int WPQ>
+__global__ void __launch_bounds__(TcCfg<WPQ>::THREADS, 1)
+k_edge_layer_tc(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap emap, const TcParams P) {
+  edge_layer_tc_body<WPQ>(wmap, emap, P);
+}
+__global__ void __launch_bounds__(TcCfg<4>::THREADS, 1)
+k_edge_layer_tc16w(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap emap, const TcParams P) {
+  edge_layer_tc_body<4>(wmap, emap, P);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -825,7 +934,7 @@ struct TcState {
   float* lin_out = nullptr;
   const float* lin_bias = nullptr;
   int lin_rows = 0;
-  int wpq = 2;                  // worker warps per TMEM lane quarter (DFB_TC_WPQ, tuning knob)
+  int wpq = 4;                  // worker warps per TMEM lane quarter (DFB_TC_WPQ tuning knob: 1, 2 or 4)
   unsigned long long* phase_cycles = nullptr;
 };
 
@@ -838,14 +947,16 @@ inline int tc_init(TcState* st, int num_sms) {
   cudaError_t e = cudaFuncSetAttribute(k_edge_layer_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<1>::SMEM_ALLOC);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(k_edge_layer_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<2>::SMEM_ALLOC);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(k_edge_layer_tc16w, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<4>::SMEM_ALLOC);
   if (e != cudaSuccess) {
     st->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e);
     return -2;
   }
   {
     const char* w = getenv("DFB_TC_WPQ");
-    st->wpq = w ? atoi(w) : 2;
-    if (st->wpq != 1 && st->wpq != 2) st->wpq = 2;
+    st->wpq = w ? atoi(w) : 4;
+    if (st->wpq != 1 && st->wpq != 2 && st->wpq != 4) st->wpq = 4;
   }
   if ((e = cudaMalloc(&st->zero_row, H * sizeof(float))) != cudaSuccess ||
       (e = cudaMemset(st->zero_row, 0, H * sizeof(float))) != cudaSuccess ||
@@ -935,6 +1046,7 @@ inline int tc_launch_edge_layer(TcState* st, int l, float* e, const float* uvab,
   }
   int grid = P.n_tiles < st->num_sms ? P.n_tiles : st->num_sms;
   if (st->wpq == 1) k_edge_layer_tc<1><<<grid, TcCfg<1>::THREADS, TcCfg<1>::SMEM_ALLOC, stream>>>(st->wmap, st->emap, P);
+  else if (st->wpq == 4) k_edge_layer_tc16w<<<grid, TcCfg<4>::THREADS, TcCfg<4>::SMEM_ALLOC, stream>>>(st->wmap, st->emap, P);
   else k_edge_layer_tc<2><<<grid, TcCfg<2>::THREADS, TcCfg<2>::SMEM_ALLOC, stream>>>(st->wmap, st->emap, P);
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) {

@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out; rm -f gpurun_out/probe10.log
+for W in 4 2; do
+  echo "=== WPQ=$W parity subset ==="
+  DFB_TC_WPQ=$W timeout 600 python -m pytest tests/test_gpu_parity.py -q -m gpu -x -k "tc_gemm or (tc and (forward_tsp_categorical_golden or forward_tsp_gaussian_golden or traj_tsp_cat or traj_mis_cat or forward_mis_golden or forward_tsp_vs_oracle or forward_dense or tsp500_full))" 2>&1 | tail -6 | tee gpurun_out/t10_w$W.log
+  DFB_TC_WPQ=$W DFB_TC_PROBE=128 timeout 300 python scripts/probe_tc.py fwd 2>&1 | grep -E "probe=" | sed "s/^/WPQ=$W /" | tee -a gpurun_out/probe10.log
+done

@@ -8,5 +8,5 @@ timeout 900 python bench.py --steps 3 --warmup 3 2>&1 | tail -1 | tee gpurun_out
 echo "=== ncu launch list on the denoise loop ==="
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 120 -c 120 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1
 echo "=== ncu full, one edge-kernel launch at full size ==="
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_edge_layer_tc -s 30 -c 1 -o gpurun_out/edge_full python bench.py --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_edge_layer_tc16w -s 30 -c 1 -o gpurun_out/edge_full python bench.py --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
 ls -la gpurun_out | tail -4
