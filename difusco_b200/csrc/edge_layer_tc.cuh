@@ -270,6 +270,7 @@ struct TcCfg {
   static constexpr int CPP = H / WPQ;                     // columns per part
   static constexpr int PATCH_COLS = (WPQ == 4) ? 8 : 16;  // columns per segment-reduce pass (E1 sub-chunk = 16 columns)
   static constexpr int CW = (WPQ == 4) ? 16 : 32;         // TMEM chunk width of E2/E3/E4 (register budget)
+  static_assert((TC_KCH / WPQ) % CW == 0, "a part's slice of a K-chunk must be whole TMEM chunks");
   static constexpr bool PREFETCH = (WPQ != 4);            // register prefetch of the next sub-chunk (register budget)
   static constexpr bool GATE_B0 = (WPQ == 4);             // gather buffers spill into B0: GEMM2's first weights wait for E1
   static constexpr int OFF_PATCH = TC_OFF_PRM + 6 * H * 4;   // per warp PATCH_COLS x 36 floats; also carries the LN statistics
@@ -295,7 +296,7 @@ __device__ __forceinline__ void edge_layer_tc_body(const CUtensorMap& wmap, cons
   const float** s_src = reinterpret_cast<const float**>(smem + Cfg::OFF_SRC);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
   uint64_t* full_a1 = bars;       // [2] all workers -> MMA (GEMM1 A chunks, NWORK arrivals)
-  uint64_t* full_a2 = bars + 2;   // [2] owning part  -> MMA (GEMM2 A chunks, 128 arrivals)
+  uint64_t* full_a2 = bars + 2;   // [2] all workers -> MMA (GEMM2 A chunks, NWORK arrivals)
   uint64_t* full_b = bars + 4;    // [2] TMA -> MMA (expect_tx)
   uint64_t* empty = bars + 6;     // [2] MMA commit -> producer + workers
   uint64_t* acc_rdy = bars + 8;   // [2] MMA commit -> workers (GEMM1 / GEMM2 accumulator complete)
@@ -309,7 +310,7 @@ __device__ __forceinline__ void edge_layer_tc_body(const CUtensorMap& wmap, cons
 
   if (threadIdx.x == 0) {
     mbar_init(&full_a1[0], Cfg::NWORK); mbar_init(&full_a1[1], Cfg::NWORK);
-    mbar_init(&full_a2[0], 128);        mbar_init(&full_a2[1], 128);
+    mbar_init(&full_a2[0], Cfg::NWORK); mbar_init(&full_a2[1], Cfg::NWORK);
     mbar_init(&full_b[0], 1);           mbar_init(&full_b[1], 1);
     mbar_init(&empty[0], 1);            mbar_init(&empty[1], 1);
     mbar_init(&acc_rdy[0], 1);          mbar_init(&acc_rdy[1], 1);
@@ -360,9 +361,7 @@ __device__ __forceinline__ void edge_layer_tc_body(const CUtensorMap& wmap, cons
           const uint32_t dst = smem_base + tc_off_b(s);
           // C_hi,C_lo | O_hi,O_lo blocks of 256 rows; linear mode: U|V|A|B (hi,lo) blocks follow at +1024
           const int rb = P.lin_out ? P.w_row_base + 1024 + (tile & 3) * 512 : P.w_row_base + (i < 4 ? 0 : 512);
-          // GEMM2 consumes its K-chunks in the order 0,2,1,3 so that with two column parts (chunks {0,1} and {2,3})
-          // both parts' first chunks feed the tensor core while E3 is still producing the second ones
-          const int kw = (WPQ != 4 && i >= 4 && !P.lin_out) ? ((kc & 1) * 2 + (kc >> 1)) : kc;
+          const int kw = kc;
           tma_load_2d(dst, &wmap, &full_b[s], kw * TC_KCH, rb);
           tma_load_2d(dst + TC_B_BYTES, &wmap, &full_b[s], kw * TC_KCH, rb + 256);
         }
@@ -696,10 +695,10 @@ __device__ __forceinline__ void edge_layer_tc_body(const CUtensorMap& wmap, cons
       if (!P.write_e) {   // MIS last layer: edge stream is dead (gnn_encoder.py:412)
         tmem_wait_ld();
         tc_fence_before();
-        if constexpr (Cfg::GATE_B0) {   // gather buffers (in B0) are dead once every warp has left E1
-          worker_bar();
-          if (wt == 0) mbar_arrive(e1_done);
-        }
+        // every warp must have left E1 before the next tile's setup overwrites s_row / s_col (read by E1's gather
+        // setup and segment flush); with GATE_B0 this also marks the gather buffers in B0 dead
+        worker_bar();
+        if (Cfg::GATE_B0 && wt == 0) mbar_arrive(e1_done);
         continue;
       }
       tmem_wait_st();
@@ -791,16 +790,17 @@ __device__ __forceinline__ void edge_layer_tc_body(const CUtensorMap& wmap, cons
       PHASE(3);   // E2
       // ---------------- E3: s = silu(LN_O(e_til)) -> GEMM2 A operand chunks (this part's K-chunks) ----------------
 #pragma unroll 1
-      for (int idx = 0; idx < 4 / WPQ; ++idx) {
-        const int pos = part + idx * WPQ;                  // position in GEMM2's consumption order 0,2,1,3
-        const int kc = (WPQ == 4) ? pos : (pos & 1) * 2 + (pos >> 1);   // K-chunk (64 columns of s) at that position
-        const uint32_t u = u_tile + 4 + pos;
+      // every K-chunk (64 columns of s) is produced cooperatively: part p converts columns [64 kc + p*64/WPQ, +64/WPQ),
+      // so chunk 0 is complete after 1/4 of E3 and GEMM2 runs underneath the rest of E3
+      for (int kc = 0; kc < 4; ++kc) {
+        const uint32_t u = u_tile + 4 + kc;
         const int s = u & 1, k = u >> 1;
         unsigned char* a_hi = smem + tc_off_a(s);
         unsigned char* a_lo = a_hi + TC_A_BYTES;
 #pragma unroll 1
-        for (int piece = 0; piece < TC_KCH / Cfg::CW; ++piece) {
-          const int c0 = kc * TC_KCH + piece * Cfg::CW;
+        for (int piece = 0; piece < (TC_KCH / WPQ) / Cfg::CW; ++piece) {
+          const int cc = part * (TC_KCH / WPQ) + piece * Cfg::CW;   // column offset inside the 64-column chunk
+          const int c0 = kc * TC_KCH + cc;
           uint32_t v[Cfg::CW];
           tmem_ldN<Cfg::CW>(t_acc1 + c0, v);
           tmem_wait_ld();
@@ -822,7 +822,7 @@ __device__ __forceinline__ void edge_layer_tc_body(const CUtensorMap& wmap, cons
             uint2 h0, l0, h1, l1;
             split4(make_float4(z[0], z[1], z[2], z[3]), h0, l0);
             split4(make_float4(z[4], z[5], z[6], z[7]), h1, l1);
-            const uint32_t off = sw128_off(r, piece * (Cfg::CW / 8) + j);
+            const uint32_t off = sw128_off(r, (cc >> 3) + j);
             *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(h0.x, h0.y, h1.x, h1.y);
             *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(l0.x, l0.y, l1.x, l1.y);
           }

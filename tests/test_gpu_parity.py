@@ -373,3 +373,24 @@ def test_config5_tsp10000_full_size_properties(weights2):
   reps = a.reshape(4, -1)
   for p in range(1, 4):
     assert np.abs(reps[p] - reps[0]).max() < 1e-5
+
+
+def test_repeated_runs_bitwise_identical(weights2):
+  """Race detector: the path has no atomics and a fixed summation structure, so repeated forwards over multi-tile
+  graphs (persistent CTAs looping over tiles, MIS last layer without GEMM2, TSP with the TMA store path) must be
+  bitwise identical.  A synchronisation bug between the tile phases shows up here as run-to-run noise."""
+  ei, sizes = syn.mis_batch(700, 800, 0.15, 2, seed=43)
+  V = sum(sizes)
+  xt = (syn.initial_noise(V, 12) > 0).astype(np.float32)
+  enc = G.encoder(weights2, 2, node_only=True, impl="tc")
+  first = enc(G.cu(xt), torch.tensor([100.0]), edge_index=G.cu(ei)).cpu().numpy()
+  for _ in range(6):
+    again = enc(G.cu(xt), torch.tensor([100.0]), edge_index=G.cu(ei)).cpu().numpy()
+    assert np.array_equal(first, again)
+  pts, eit = syn.tsp_sparse_batch(500, 50, 8, seed=77)
+  xte = (syn.initial_noise(eit.shape[1], 13) > 0).astype(np.float32)
+  enc2 = G.encoder(weights2, 2, impl="tc")
+  a = enc2(G.cu(pts), torch.tensor([640.0]), G.cu(xte), G.cu(eit)).cpu().numpy()
+  for _ in range(6):
+    b = enc2(G.cu(pts), torch.tensor([640.0]), G.cu(xte), G.cu(eit)).cpu().numpy()
+    assert np.array_equal(a, b)
