@@ -299,7 +299,8 @@ def run_ours(args, rank, world, local_rank):
             "data": "synthetic", "config": workload_config(world),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
-                         "kernel": "k_edge_layer_tc" if os.environ.get("DFB_EDGE_IMPL", "tc") != "fp32" else "k_edge_layer_fp32",
+                         "kernel": ("k_edge_layer_tc16w" if os.environ.get("DFB_TC_WPQ", "4") == "4" else "k_edge_layer_tc<%s>" % os.environ.get("DFB_TC_WPQ"))
+                                   if os.environ.get("DFB_EDGE_IMPL", "tc") != "fp32" else "k_edge_layer_fp32",
                          "algorithmic_bytes_per_launch": (2 * L - 1) * E * H * 4 / L,
                          "launches_timed": int(edge_n), "kernel_ms_total": edge_ms,
                          "kernel_share_of_step": edge_ms / total_ms},

@@ -120,6 +120,14 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(TC_IDESC), "r"(accumulate)
       : "memory");
 }
+// A operand from tensor memory (lane = row, 32-bit columns = packed bf16 pairs along K), B from shared memory
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
+      " tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(TC_IDESC), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
@@ -381,13 +389,26 @@ __device__ __forceinline__ void edge_layer_tc_body(const CUtensorMap& wmap, cons
           const uint32_t a_hi = smem_base + tc_off_a(s), a_lo = a_hi + TC_A_BYTES;
           const uint32_t b_hi = smem_base + tc_off_b(s), b_lo = b_hi + TC_B_BYTES;
           const uint32_t d = tmem_base + (i < 4 ? 0u : 256u);
+          if (i < 4) {
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t dah = umma_desc_sw128(a_hi + ks * 32), dal = umma_desc_sw128(a_lo + ks * 32);
-            const uint64_t dbh = umma_desc_sw128(b_hi + ks * 32), dbl = umma_desc_sw128(b_lo + ks * 32);
-            umma_bf16(d, dah, dbh, (kc | ks) ? 1u : 0u);
-            umma_bf16(d, dal, dbh, 1u);
-            umma_bf16(d, dah, dbl, 1u);
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint64_t dah = umma_desc_sw128(a_hi + ks * 32), dal = umma_desc_sw128(a_lo + ks * 32);
+              const uint64_t dbh = umma_desc_sw128(b_hi + ks * 32), dbl = umma_desc_sw128(b_lo + ks * 32);
+              umma_bf16(d, dah, dbh, (kc | ks) ? 1u : 0u);
+              umma_bf16(d, dal, dbh, 1u);
+              umma_bf16(d, dah, dbl, 1u);
+            }
+          } else {
+            // GEMM2: the A operand (bf16 hi/lo of s) was written by E3 IN PLACE over e_til in the GEMM1 accumulator
+            // columns: k-step ks of chunk kc sits at columns 64 kc + 16 ks (8 columns hi, 8 columns lo)
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint32_t ta_hi = tmem_base + kc * 64 + ks * 16, ta_lo = ta_hi + 8;
+              const uint64_t dbh = umma_desc_sw128(b_hi + ks * 32), dbl = umma_desc_sw128(b_lo + ks * 32);
+              umma_bf16_ts(d, ta_hi, dbh, (kc | ks) ? 1u : 0u);
+              umma_bf16_ts(d, ta_lo, dbh, 1u);
+              umma_bf16_ts(d, ta_hi, dbl, 1u);
+            }
           }
           umma_commit(&empty[s]);                       // frees the stage when these MMAs have read it
           if (kc == 3) umma_commit(&acc_rdy[i < 4 ? 0 : 1]);
@@ -564,8 +585,8 @@ __device__ __forceinline__ void edge_layer_tc_body(const CUtensorMap& wmap, cons
       const float4* pb = reinterpret_cast<const float4*>(uv_row + 3 * H + cbase);
       uint32_t vn[16];
       float4 bn[4];
+      if constexpr (Cfg::PREFETCH) tmem_ld16(t_acc1 + cbase, vn);
       if constexpr (Cfg::PREFETCH) {
-        tmem_ld16(t_acc1 + cbase, vn);
 #pragma unroll
         for (int j = 0; j < 4; ++j) bn[j] = __ldg(pb + j);
       }
@@ -582,15 +603,18 @@ __device__ __forceinline__ void edge_layer_tc_body(const CUtensorMap& wmap, cons
           tmem_wait_ld();
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = vn[j];
+          if (sub + 1 < NSUB) tmem_ld16(t_acc1 + c0 + 16, vn);
+        } else {
+          tmem_ld16(t_acc1 + c0, v);
+        }
+        if constexpr (Cfg::PREFETCH) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) bb[j] = bn[j];
-          if (sub + 1 < NSUB) {               // prefetch the next sub-chunk
-            tmem_ld16(t_acc1 + c0 + 16, vn);
+          if (sub + 1 < NSUB) {             // B h[row] of the next sub-chunk: an L2 round trip hidden behind this one
 #pragma unroll
             for (int j = 0; j < 4; ++j) bn[j] = __ldg(pb + 4 * (sub + 1) + j);
           }
-        } else {
-          tmem_ld16(t_acc1 + c0, v);
+        } else {                            // 16-warp variant: no register room for the prefetch
 #pragma unroll
           for (int j = 0; j < 4; ++j) bb[j] = __ldg(pb + 4 * sub + j);
           tmem_wait_ld();
@@ -794,9 +818,7 @@ __device__ __forceinline__ void edge_layer_tc_body(const CUtensorMap& wmap, cons
       // so chunk 0 is complete after 1/4 of E3 and GEMM2 runs underneath the rest of E3
       for (int kc = 0; kc < 4; ++kc) {
         const uint32_t u = u_tile + 4 + kc;
-        const int s = u & 1, k = u >> 1;
-        unsigned char* a_hi = smem + tc_off_a(s);
-        unsigned char* a_lo = a_hi + TC_A_BYTES;
+        const int s = u & 1;
 #pragma unroll 1
         for (int piece = 0; piece < (TC_KCH / WPQ) / Cfg::CW; ++piece) {
           const int cc = part * (TC_KCH / WPQ) + piece * Cfg::CW;   // column offset inside the 64-column chunk
@@ -804,30 +826,34 @@ __device__ __forceinline__ void edge_layer_tc_body(const CUtensorMap& wmap, cons
           uint32_t v[Cfg::CW];
           tmem_ldN<Cfg::CW>(t_acc1 + c0, v);
           tmem_wait_ld();
-          if (piece == 0) mbar_wait(&empty[s], (k & 1) ^ 1, P.error_flag, 6);
 #pragma unroll
-          for (int j = 0; j < Cfg::CW / 8; ++j) {   // 16-byte units of 8 bf16
-            float z[8];
+          for (int g16 = 0; g16 < Cfg::CW / 16; ++g16) {   // one MMA k-step (16 elements) = 8 columns hi + 8 columns lo
+            uint32_t w16[16];
 #pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-              const float4 g4 = *reinterpret_cast<const float4*>(prm + 3 * H + c0 + 8 * j + 4 * hh);
-              const float4 b4 = *reinterpret_cast<const float4*>(prm + 4 * H + c0 + 8 * j + 4 * hh);
-              const float2 t01 = fma2(fma2(make_float2(__uint_as_float(v[8 * j + 4 * hh]), __uint_as_float(v[8 * j + 4 * hh + 1])),
-                                           rs2, nm2), make_float2(g4.x, g4.y), make_float2(b4.x, b4.y));
-              const float2 t23 = fma2(fma2(make_float2(__uint_as_float(v[8 * j + 4 * hh + 2]), __uint_as_float(v[8 * j + 4 * hh + 3])),
-                                           rs2, nm2), make_float2(g4.z, g4.w), make_float2(b4.z, b4.w));
-              const float2 s01 = mul2(t01, sigmoid_mufu2(t01)), s23 = mul2(t23, sigmoid_mufu2(t23));   // SiLU
-              z[4 * hh] = s01.x; z[4 * hh + 1] = s01.y; z[4 * hh + 2] = s23.x; z[4 * hh + 3] = s23.y;
+            for (int j = 0; j < 2; ++j) {               // 8 elements each
+              float z[8];
+#pragma unroll
+              for (int hh = 0; hh < 2; ++hh) {
+                const int e0 = 16 * g16 + 8 * j + 4 * hh;
+                const float4 g4 = *reinterpret_cast<const float4*>(prm + 3 * H + c0 + e0);
+                const float4 b4 = *reinterpret_cast<const float4*>(prm + 4 * H + c0 + e0);
+                const float2 t01 = fma2(fma2(make_float2(__uint_as_float(v[e0]), __uint_as_float(v[e0 + 1])), rs2, nm2),
+                                        make_float2(g4.x, g4.y), make_float2(b4.x, b4.y));
+                const float2 t23 = fma2(fma2(make_float2(__uint_as_float(v[e0 + 2]), __uint_as_float(v[e0 + 3])), rs2, nm2),
+                                        make_float2(g4.z, g4.w), make_float2(b4.z, b4.w));
+                const float2 s01 = mul2(t01, sigmoid_mufu2(t01)), s23 = mul2(t23, sigmoid_mufu2(t23));   // SiLU
+                z[4 * hh] = s01.x; z[4 * hh + 1] = s01.y; z[4 * hh + 2] = s23.x; z[4 * hh + 3] = s23.y;
+              }
+              uint2 h0, l0, h1, l1;
+              split4(make_float4(z[0], z[1], z[2], z[3]), h0, l0);
+              split4(make_float4(z[4], z[5], z[6], z[7]), h1, l1);
+              w16[4 * j] = h0.x; w16[4 * j + 1] = h0.y; w16[4 * j + 2] = h1.x; w16[4 * j + 3] = h1.y;             // hi: columns 0..7
+              w16[8 + 4 * j] = l0.x; w16[8 + 4 * j + 1] = l0.y; w16[8 + 4 * j + 2] = l1.x; w16[8 + 4 * j + 3] = l1.y;   // lo: columns 8..15
             }
-            uint2 h0, l0, h1, l1;
-            split4(make_float4(z[0], z[1], z[2], z[3]), h0, l0);
-            split4(make_float4(z[4], z[5], z[6], z[7]), h1, l1);
-            const uint32_t off = sw128_off(r, (cc >> 3) + j);
-            *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(h0.x, h0.y, h1.x, h1.y);
-            *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+            tmem_st16(t_acc1 + c0 + 16 * g16, w16);
           }
         }
-        fence_proxy_async();
+        tmem_wait_st();
         tc_fence_before();
         mbar_arrive(&full_a2[s]);
       }
