@@ -19,7 +19,7 @@ SYMBOLS = [
     "dfb_set_edge_impl", "dfb_load_weights", "dfb_prepare_graph", "dfb_set_points",
     "dfb_encoder_forward", "dfb_denoise_step", "dfb_denoise", "dfb_denoise_host",
     "dfb_launch_count", "dfb_profile_begin", "dfb_profile_end", "dfb_debug_edge_gemm",
-    "dfb_debug_phase_cycles",
+    "dfb_debug_phase_cycles", "dfb_debug_watchdog",
 ]
 
 _lib = None
@@ -58,6 +58,7 @@ def lib():
   L.dfb_profile_end.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64)]
   L.dfb_debug_edge_gemm.argtypes = [vp, i32, vp, vp, vp]
   L.dfb_debug_phase_cycles.argtypes = [vp, C.POINTER(C.c_uint64)]
+  L.dfb_debug_watchdog.argtypes = [vp, C.POINTER(C.c_int)]
   for name in SYMBOLS:
     fn = getattr(L, name)
     if fn.restype is C.c_int and name not in ("dfb_abi_version",):
@@ -179,6 +180,11 @@ class Context(object):
     ms, n = C.c_double(0), C.c_int64(0)
     self._ck(lib().dfb_profile_end(self._h, C.byref(ms), C.byref(n)))
     return ms.value, n.value
+
+  def debug_watchdog(self):
+    out = (C.c_int * 4)()
+    lib().dfb_debug_watchdog(self._h, out)
+    return [int(x) for x in out]
 
   def debug_phase_cycles(self):
     out = (C.c_uint64 * 16)()

@@ -663,7 +663,7 @@ static int run_forward(dfb_ctx* ctx, const float* xt, const float* tvec, bool bi
   const int bps = (rps + GN_ROWS_PER_BLOCK - 1) / GN_ROWS_PER_BLOCK;
   k_gn_partial<<<dim3(bps, ctx->gn_segments), 256, 0, st>>>(Z, rps, (double*)ctx->gn_part.p);
   CKL(ctx);
-  k_gn_final<<<ctx->gn_segments, 1024, 0, st>>>((const double*)ctx->gn_part.p, bps, rps, (float*)ctx->gn_stats.p);
+  k_gn_final<<<dim3(ctx->gn_segments, 32), 256, 0, st>>>((const double*)ctx->gn_part.p, bps, rps, (float*)ctx->gn_stats.p);
   CKL(ctx);
   k_head<<<(R + 255) / 256, 256, 0, st>>>(Z, R, rps, (const float*)ctx->gn_stats.p, ctx->node_only ? nullptr : g.perm,
                                       ctx->hp, pa);
@@ -831,5 +831,13 @@ extern "C" int dfb_debug_phase_cycles(dfb_ctx* ctx, unsigned long long* out) {
   CK(ctx, cudaDeviceSynchronize());
   CK(ctx, cudaMemcpy(out, ctx->tc.phase_cycles, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   CK(ctx, cudaMemset(ctx->tc.phase_cycles, 0, 16 * sizeof(unsigned long long)));
+  return DFB_OK;
+}
+
+// Diagnostic: watchdog record of the tcgen05 kernel (host-mapped, readable even after a launch failure):
+// out[0] = wait-site code (0 = none), out[1] = blockIdx.x, out[2] = parity waited for, out[3] = threadIdx.x.
+extern "C" int dfb_debug_watchdog(dfb_ctx* ctx, int* out) {
+  if (!ctx || !out || !ctx->tc.error_host) return DFB_E_INVALID;
+  for (int i = 0; i < 4; ++i) out[i] = ((volatile int*)ctx->tc.error_host)[i];
   return DFB_OK;
 }

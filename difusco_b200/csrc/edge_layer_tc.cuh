@@ -97,7 +97,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* e
         : "memory");
     if (ok) return;
     if (spin > 400000u) {   // >> any legitimate wait (each failed try_wait already slept up to 20 us)
-      if (error_flag) atomicExch(error_flag, code);
+      if (error_flag) {
+        error_flag[1] = (int)blockIdx.x;
+        error_flag[2] = (int)parity;
+        error_flag[3] = (int)threadIdx.x;
+        atomicExch(error_flag, code);
+      }
       __threadfence_system();
       __trap();
     }
@@ -303,15 +308,18 @@ __device__ __forceinline__ void edge_layer_tc_body(const CUtensorMap& wmap, cons
   int* s_col = reinterpret_cast<int*>(smem + Cfg::OFF_COL);
   const float** s_src = reinterpret_cast<const float**>(smem + Cfg::OFF_SRC);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
-  uint64_t* full_a1 = bars;       // [2] all workers -> MMA (GEMM1 A chunks, NWORK arrivals)
-  uint64_t* full_a2 = bars + 2;   // [2] all workers -> MMA (GEMM2 A chunks, NWORK arrivals)
-  uint64_t* full_b = bars + 4;    // [2] TMA -> MMA (expect_tx)
-  uint64_t* empty = bars + 6;     // [2] MMA commit -> producer + workers
-  uint64_t* acc_rdy = bars + 8;   // [2] MMA commit -> workers (GEMM1 / GEMM2 accumulator complete)
-  uint64_t* ein_bar = bars + 10;  // TMA load of the residual tile (expect_tx)
-  uint64_t* e4_done = bars + 11;  // staging (A0|A1|B0) released after the TMA store has read it
-  uint64_t* e1_done = bars + 12;  // all warps left E1: the B0 region no longer holds gather buffers (GATE_B0)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  uint64_t* full_a1 = bars;       // [2] all workers -> MMA (GEMM1 A chunks in smem stage s, NWORK arrivals)
+  uint64_t* full_a2 = bars + 2;   // [4] all workers -> MMA (GEMM2 A chunk kc written to TMEM).  One barrier PER CHUNK,
+                                  //     completing once per tile: E3 has no back-pressure from the MMA any more (the A
+                                  //     operand lives in TMEM, no stage to wait for), so two chunks must never share a
+                                  //     barrier - the workers could run two phases ahead of the MMA thread's parity wait.
+  uint64_t* full_b = bars + 6;    // [2] TMA -> MMA (expect_tx)
+  uint64_t* empty = bars + 8;     // [2] MMA commit -> producer + workers
+  uint64_t* acc_rdy = bars + 10;  // [2] MMA commit -> workers (GEMM1 / GEMM2 accumulator complete)
+  uint64_t* ein_bar = bars + 12;  // TMA load of the residual tile (expect_tx)
+  uint64_t* e4_done = bars + 13;  // staging (A0|A1|B0) released after the TMA store has read it
+  uint64_t* e1_done = bars + 14;  // all warps left E1: the B0 region no longer holds gather buffers (GATE_B0)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int uses_per_tile = P.write_e ? 8 : 4;
@@ -319,6 +327,7 @@ __device__ __forceinline__ void edge_layer_tc_body(const CUtensorMap& wmap, cons
   if (threadIdx.x == 0) {
     mbar_init(&full_a1[0], Cfg::NWORK); mbar_init(&full_a1[1], Cfg::NWORK);
     mbar_init(&full_a2[0], Cfg::NWORK); mbar_init(&full_a2[1], Cfg::NWORK);
+    mbar_init(&full_a2[2], Cfg::NWORK); mbar_init(&full_a2[3], Cfg::NWORK);
     mbar_init(&full_b[0], 1);           mbar_init(&full_b[1], 1);
     mbar_init(&empty[0], 1);            mbar_init(&empty[1], 1);
     mbar_init(&acc_rdy[0], 1);          mbar_init(&acc_rdy[1], 1);
@@ -378,13 +387,15 @@ __device__ __forceinline__ void edge_layer_tc_body(const CUtensorMap& wmap, cons
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
     if (lane == 0) {
-      uint32_t u = 0;
-      for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+      uint32_t u = 0, tile_it = 0;
+      for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++tile_it) {
         for (int i = 0; i < uses_per_tile; ++i, ++u) {
           const int s = u & 1, k = u >> 1, kc = i & 3;
           mbar_wait(&full_b[s], k & 1, P.error_flag, 2);
-          // each A barrier of a stage completes twice per tile (chunks kc, kc+2): parity (kc>>1)&1
-          mbar_wait(i < 4 ? &full_a1[s] : &full_a2[s], (kc >> 1) & 1, P.error_flag, 3);
+          // full_a1[s] completes twice per tile (chunks kc, kc+2; conv waits for empty[s] in between): parity (kc>>1)&1.
+          // full_a2[kc] completes once per tile: parity tile_it & 1.
+          if (i < 4) mbar_wait(&full_a1[s], (kc >> 1) & 1, P.error_flag, 3);
+          else mbar_wait(&full_a2[kc], tile_it & 1, P.error_flag, 13);
           tc_fence_after();
           const uint32_t a_hi = smem_base + tc_off_a(s), a_lo = a_hi + TC_A_BYTES;
           const uint32_t b_hi = smem_base + tc_off_b(s), b_lo = b_hi + TC_B_BYTES;
@@ -817,8 +828,6 @@ __device__ __forceinline__ void edge_layer_tc_body(const CUtensorMap& wmap, cons
       // every K-chunk (64 columns of s) is produced cooperatively: part p converts columns [64 kc + p*64/WPQ, +64/WPQ),
       // so chunk 0 is complete after 1/4 of E3 and GEMM2 runs underneath the rest of E3
       for (int kc = 0; kc < 4; ++kc) {
-        const uint32_t u = u_tile + 4 + kc;
-        const int s = u & 1;
 #pragma unroll 1
         for (int piece = 0; piece < (TC_KCH / WPQ) / Cfg::CW; ++piece) {
           const int cc = part * (TC_KCH / WPQ) + piece * Cfg::CW;   // column offset inside the 64-column chunk
@@ -855,7 +864,7 @@ __device__ __forceinline__ void edge_layer_tc_body(const CUtensorMap& wmap, cons
         }
         tmem_wait_st();
         tc_fence_before();
-        mbar_arrive(&full_a2[s]);
+        mbar_arrive(&full_a2[kc]);
       }
 
       PHASE(4);   // E3
@@ -954,7 +963,8 @@ struct TcState {
   bool bound = false;
   int last_launches = 0;
   float* zero_row = nullptr;
-  int* error_flag = nullptr;
+  int* error_flag = nullptr;    // device alias of error_host (host-mapped: readable after a trap)
+  int* error_host = nullptr;
   float* debug_acc = nullptr;   // set by the debug entry point for one launch
   const float* lin_in = nullptr;   // linear mode arguments, set for one launch by tc_launch_linear
   float* lin_out = nullptr;
@@ -988,8 +998,8 @@ inline int tc_init(TcState* st, int num_sms) {
       (e = cudaMemset(st->zero_row, 0, H * sizeof(float))) != cudaSuccess ||
       (e = cudaMalloc(&st->phase_cycles, 16 * sizeof(unsigned long long))) != cudaSuccess ||
       (e = cudaMemset(st->phase_cycles, 0, 16 * sizeof(unsigned long long))) != cudaSuccess ||
-      (e = cudaMalloc(&st->error_flag, sizeof(int))) != cudaSuccess ||
-      (e = cudaMemset(st->error_flag, 0, sizeof(int))) != cudaSuccess) {
+      (e = cudaHostAlloc(&st->error_host, 4 * sizeof(int), cudaHostAllocMapped)) != cudaSuccess ||
+      (e = cudaHostGetDevicePointer((void**)&st->error_flag, st->error_host, 0)) != cudaSuccess) {
     st->err = std::string("tc_init alloc: ") + cudaGetErrorString(e);
     return -2;
   }
@@ -998,10 +1008,11 @@ inline int tc_init(TcState* st, int num_sms) {
 
 inline void tc_destroy(TcState* st) {
   if (st->zero_row) cudaFree(st->zero_row);
-  if (st->error_flag) cudaFree(st->error_flag);
+  if (st->error_host) cudaFreeHost(st->error_host);
   if (st->phase_cycles) cudaFree(st->phase_cycles);
   st->zero_row = nullptr;
   st->error_flag = nullptr;
+  st->error_host = nullptr;
 }
 
 // One tensor map over the whole bf16 weight arena: [L*12*256 rows][256 K], rows of layer l are

@@ -227,19 +227,25 @@ __global__ void __launch_bounds__(256) k_gn_partial(const float* __restrict__ Z,
     part[o + 1] = Q;
   }
 }
-__global__ void __launch_bounds__(1024) k_gn_final(const double* __restrict__ part, int blocks_per_seg, int rows_per_seg,
-                                                   float* __restrict__ stats /* [segs][32][2] mean, rstd */) {
-  // one warp per group; lanes stride over the per-block partials, then a fixed-shape fp64 tree: deterministic
-  int seg = blockIdx.x, gidx = threadIdx.x >> 5, lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(256) k_gn_final(const double* __restrict__ part, int blocks_per_seg, int rows_per_seg,
+                                                  float* __restrict__ stats /* [segs][32][2] mean, rstd */) {
+  // grid (segs, 32 groups); 256 threads stride over the per-block partials, then a fixed-shape fp64 tree
+  // (warp shuffles + 8 warp results in shared memory): deterministic
+  __shared__ double sh[8][2];
+  const int seg = blockIdx.x, gidx = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   double S = 0.0, Q = 0.0;
-  for (int b = lane; b < blocks_per_seg; b += 32) {
+  for (int b = threadIdx.x; b < blocks_per_seg; b += 256) {
     size_t o = (((size_t)seg * blocks_per_seg + b) * 32 + gidx) * 2;
     S += part[o];
     Q += part[o + 1];
   }
   S = warp_sum_d(S);
   Q = warp_sum_d(Q);
-  if (lane == 0) {
+  if (lane == 0) { sh[w][0] = S; sh[w][1] = Q; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    S = 0.0; Q = 0.0;
+    for (int i = 0; i < 8; ++i) { S += sh[i][0]; Q += sh[i][1]; }
     double n = (double)rows_per_seg * 8.0;
     double mean = S / n;
     double var = Q / n - mean * mean;

@@ -131,6 +131,10 @@ int dfb_debug_edge_gemm(dfb_ctx* ctx, int layer, const float* e_in, float* acc_o
 /* Tuning hook: per-phase cycle counters of the tcgen05 edge kernel (DFB_TC_PROBE bit 7); out[8], host. */
 int dfb_debug_phase_cycles(dfb_ctx* ctx, unsigned long long* out);
 
+/* Diagnostic: watchdog record of the tcgen05 kernel's bounded barrier waits (host-mapped memory, readable after a
+ * launch failure): out[4] = {wait-site code or 0, blockIdx.x, parity, threadIdx.x}. */
+int dfb_debug_watchdog(dfb_ctx* ctx, int* out);
+
 #ifdef __cplusplus
 }
 #endif
