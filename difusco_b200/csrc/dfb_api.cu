@@ -257,7 +257,7 @@ extern "C" int dfb_load_weights(dfb_ctx* ctx, int n_layers, int hidden_dim, int 
     size_t Wt_uvab, b_uvab, Wt_C, Wt_O, b_O, hg, hb, eg, eb, og, ob, Wt_tau, b_tau;
   };
   std::vector<LOff> lo(L);
-  std::vector<uint16_t> arena16((size_t)L * 12 * H * H);
+  std::vector<uint16_t> arena16((size_t)(L * 12 + 4) * H * H);
   const float* p;
   for (int l = 0; l < L; ++l) {
     std::string pre = "layers." + std::to_string(l) + ".";
@@ -309,8 +309,18 @@ extern "C" int dfb_load_weights(dfb_ctx* ctx, int n_layers, int hidden_dim, int 
   }
   size_t o_node_W, o_node_b, o_edge_W, o_edge_b, o_t0W, o_t0b, o_t2W, o_t2b, o_gng, o_gnb, o_outW, o_outb;
   GET("node_embed.weight", H * H, &p); o_node_W = put_T(p, H, H);
+  for (int i = 0; i < H * H; ++i) {
+    uint16_t hi = f2bf16_rn(p[i]);
+    arena16[(size_t)(L * 12 + 2) * H * H + i] = hi;
+    arena16[(size_t)(L * 12 + 3) * H * H + i] = f2bf16_rn(p[i] - bf16_to_f(hi));
+  }
   GET("node_embed.bias", H, &p);       o_node_b = put_v(p, H);
   GET("edge_embed.weight", H * H, &p); o_edge_W = put_T(p, H, H);
+  for (int i = 0; i < H * H; ++i) {
+    uint16_t hi = f2bf16_rn(p[i]);
+    arena16[(size_t)(L * 12 + 0) * H * H + i] = hi;
+    arena16[(size_t)(L * 12 + 1) * H * H + i] = f2bf16_rn(p[i] - bf16_to_f(hi));
+  }
   GET("edge_embed.bias", H, &p);       o_edge_b = put_v(p, H);
   GET("time_embed.0.weight", TE * H, &p); o_t0W = put_T(p, TE, H);
   GET("time_embed.0.bias", TE, &p);       o_t0b = put_v(p, TE);
@@ -516,7 +526,7 @@ static int node_linears(dfb_ctx* ctx, int l, const float* h, float* uvab, int V,
     CKL(ctx);
     return DFB_OK;
   }
-  int r = tc_launch_linear(&ctx->tc, l, h, uvab, ctx->layers[l].b_uvab, V, ctx->g, ctx->layers[l], st);
+  int r = tc_launch_linear(&ctx->tc, l * 12 * H + 4 * H, 4, h, uvab, ctx->layers[l].b_uvab, V, ctx->g, ctx->layers[l], st);
   if (r) FAIL(ctx, DFB_E_CUDA, "tcgen05 node linear: %s", ctx->tc.err.c_str());
   ctx->launches += 1;
   return DFB_OK;
@@ -528,6 +538,18 @@ static int linear_rows(dfb_ctx* ctx, const float* X, const float* Wt, const floa
   dim3 grid((R + LIN_ROWS - 1) / LIN_ROWS, N / 256);
   k_linear<<<grid, 256, 0, st>>>(X, Wt, b, Y, R, N);
   CKL(ctx);
+  return DFB_OK;
+}
+
+// embedding linears (256 -> 256): which = 0 edge_embed, 1 node_embed.  Tensor-core path unless the fp32 validation
+// implementation is selected.
+static int embed_rows(dfb_ctx* ctx, int which, const float* X, float* Y, int R, cudaStream_t st) {
+  if (ctx->edge_impl == DFB_EDGE_IMPL_FP32 || !ctx->graph_ready)
+    return linear_rows(ctx, X, which ? ctx->Wt_node : ctx->Wt_edge, which ? ctx->b_node : ctx->b_edge, Y, R, H, st);
+  int r = tc_launch_linear(&ctx->tc, (ctx->L * 12 + 2 * which) * H, 1, X, Y, which ? ctx->b_node : ctx->b_edge, R, ctx->g,
+                           ctx->layers[0], st);
+  if (r) FAIL(ctx, DFB_E_CUDA, "tcgen05 embedding linear: %s", ctx->tc.err.c_str());
+  ctx->launches += 1;
   return DFB_OK;
 }
 
@@ -549,8 +571,7 @@ extern "C" int dfb_set_points(dfb_ctx* ctx, const float* points, void* stream_) 
     int n = std::min(CH, V - v0);
     k_pos_features<<<n, H, 0, st>>>(dp + (size_t)v0 * 2, ctx->dimt128, (float*)ctx->feat.p, n);
     CKL(ctx);
-    int r = linear_rows(ctx, (const float*)ctx->feat.p, ctx->Wt_node, ctx->b_node,
-                        (float*)ctx->h0.p + (size_t)v0 * H, n, H, st);
+    int r = embed_rows(ctx, 1, (const float*)ctx->feat.p, (float*)ctx->h0.p + (size_t)v0 * H, n, st);
     if (r) return r;
   }
   // layer 0's node linears are step-invariant too
@@ -622,7 +643,7 @@ static int run_forward(dfb_ctx* ctx, const float* xt, const float* tvec, bool bi
         k_scalar_features<<<n, H, 0, st>>>(g.perm ? xt : xt + s0, g.perm ? g.perm + s0 : nullptr, ctx->dimt256,
                                            (float*)ctx->feat.p, n);
         CKL(ctx);
-        int r = linear_rows(ctx, (const float*)ctx->feat.p, ctx->Wt_edge, ctx->b_edge, e + (size_t)s0 * H, n, H, st);
+        int r = embed_rows(ctx, 0, (const float*)ctx->feat.p, e + (size_t)s0 * H, n, st);
         if (r) return r;
       }
     }
@@ -632,7 +653,7 @@ static int run_forward(dfb_ctx* ctx, const float* xt, const float* tvec, bool bi
       int n = std::min(CH, V - v0);
       k_scalar_features<<<n, H, 0, st>>>(xt + v0, nullptr, ctx->dimt256, (float*)ctx->feat.p, n);
       CKL(ctx);
-      int r = linear_rows(ctx, (const float*)ctx->feat.p, ctx->Wt_node, ctx->b_node, h + (size_t)v0 * H, n, H, st);
+      int r = embed_rows(ctx, 1, (const float*)ctx->feat.p, h + (size_t)v0 * H, n, st);
       if (r) return r;
     }
     e_zero = 1;   // gnn_encoder.py:407: e0 = zeros

@@ -60,6 +60,8 @@ struct TcParams {
   float* lin_out;
   const float* lin_bias;
   int lin_rows;
+  int lin_nb;             // 256-column output blocks per row tile: 4 (U|V|A|B) or 1 (embedding linears)
+  int lin_w_row;          // first weight row of block 0 in the bf16 arena (blocks are 512 rows apart: hi, lo)
   int* error_flag;
   int write_e, e_zero, agg_mode;
   int w_row_base;         // row of this layer's C_hi block in the bf16 weight arena tensor map
@@ -377,7 +379,7 @@ __device__ __forceinline__ void edge_layer_tc_body(const CUtensorMap& wmap, cons
           mbar_arrive_expect_tx(&full_b[s], 2 * TC_B_BYTES);
           const uint32_t dst = smem_base + tc_off_b(s);
           // C_hi,C_lo | O_hi,O_lo blocks of 256 rows; linear mode: U|V|A|B (hi,lo) blocks follow at +1024
-          const int rb = P.lin_out ? P.w_row_base + 1024 + (tile & 3) * 512 : P.w_row_base + (i < 4 ? 0 : 512);
+          const int rb = P.lin_out ? P.lin_w_row + (P.lin_nb == 4 ? (tile & 3) : 0) * 512 : P.w_row_base + (i < 4 ? 0 : 512);
           const int kw = kc;
           tma_load_2d(dst, &wmap, &full_b[s], kw * TC_KCH, rb);
           tma_load_2d(dst + TC_B_BYTES, &wmap, &full_b[s], kw * TC_KCH, rb + 256);
@@ -453,7 +455,7 @@ __device__ __forceinline__ void edge_layer_tc_body(const CUtensorMap& wmap, cons
     uint32_t u_tile = 0;
     for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, u_tile += uses_per_tile) {
       PROF_TILE_START();
-      const int s_edge = (P.lin_out ? (tile >> 2) : tile) * TC_TILE + r;
+      const int s_edge = ((P.lin_out && P.lin_nb == 4) ? (tile >> 2) : tile) * TC_TILE + r;
       const bool valid = s_edge < (P.lin_out ? P.lin_rows : P.g.E);
       int my_row = -1, my_col = 0;
       const float* src = P.zero_row;
@@ -527,7 +529,8 @@ __device__ __forceinline__ void edge_layer_tc_body(const CUtensorMap& wmap, cons
       tc_fence_after();
       PHASE(1);   // wait for GEMM1
       if (P.lin_out) {
-        const int nb = tile & 3;
+        const int nb = (P.lin_nb == 4) ? (tile & 3) : 0;
+        const int ostride = P.lin_nb * H;
 #pragma unroll 1
         for (int c0 = cbase; c0 < cbase + Cfg::CPP; c0 += 32) {
           uint32_t v[32];
@@ -535,7 +538,7 @@ __device__ __forceinline__ void edge_layer_tc_body(const CUtensorMap& wmap, cons
           tmem_wait_ld();
           if (valid) {
             const float4* bias = reinterpret_cast<const float4*>(P.lin_bias + nb * H + c0);
-            float4* dst = reinterpret_cast<float4*>(P.lin_out + (size_t)s_edge * 4 * H + nb * H + c0);
+            float4* dst = reinterpret_cast<float4*>(P.lin_out + (size_t)s_edge * ostride + nb * H + c0);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float4 b4 = __ldg(bias + j);
@@ -969,7 +972,7 @@ struct TcState {
   const float* lin_in = nullptr;   // linear mode arguments, set for one launch by tc_launch_linear
   float* lin_out = nullptr;
   const float* lin_bias = nullptr;
-  int lin_rows = 0;
+  int lin_rows = 0, lin_nb = 4, lin_w_row = 0;
   int wpq = 4;                  // worker warps per TMEM lane quarter (DFB_TC_WPQ tuning knob: 1, 2 or 4)
   unsigned long long* phase_cycles = nullptr;
 };
@@ -1016,7 +1019,8 @@ inline void tc_destroy(TcState* st) {
 }
 
 // One tensor map over the whole bf16 weight arena: [L*12*256 rows][256 K], rows of layer l are
-// C_hi | C_lo | O_hi | O_lo | U_hi | U_lo | V_hi | V_lo | A_hi | A_lo | B_hi | B_lo (256 rows each).  Box = 64 K x 256 rows, 128-byte swizzle.
+// C_hi | C_lo | O_hi | O_lo | U_hi | U_lo | V_hi | V_lo | A_hi | A_lo | B_hi | B_lo (256 rows each); after the
+// layers: edge_embed hi | lo, node_embed hi | lo.  Box = 64 K x 256 rows, 128-byte swizzle.
 inline int tc_bind_weights(TcState* st, const LayerParams* layers, int L) {
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
@@ -1026,7 +1030,7 @@ inline int tc_bind_weights(TcState* st, const LayerParams* layers, int L) {
     cudaGetLastError();
     return -2;
   }
-  cuuint64_t gdim[2] = {(cuuint64_t)H, (cuuint64_t)L * 12 * H};
+  cuuint64_t gdim[2] = {(cuuint64_t)H, (cuuint64_t)(L * 12 + 4) * H};
   cuuint64_t gstride[1] = {(cuuint64_t)H * sizeof(uint16_t)};
   cuuint32_t box[2] = {(cuuint32_t)TC_KCH, 256u};
   cuuint32_t estr[2] = {1u, 1u};
@@ -1051,7 +1055,7 @@ inline int tc_launch_edge_layer(TcState* st, int l, float* e, const float* uvab,
     return -1;
   }
   const long long e_rows = (long long)((g.E + TC_TILE - 1) / TC_TILE) * TC_TILE;
-  if (st->emap_ptr != (const void*)e || st->emap_rows != e_rows) {
+  if (!st->lin_out && (st->emap_ptr != (const void*)e || st->emap_rows != e_rows)) {   // linear mode never touches it
     cuuint64_t gdim[2] = {(cuuint64_t)H, (cuuint64_t)e_rows};
     cuuint64_t gstride[1] = {(cuuint64_t)H * sizeof(float)};
     cuuint32_t box[2] = {32u, (cuuint32_t)TC_TILE};
@@ -1075,7 +1079,8 @@ inline int tc_launch_edge_layer(TcState* st, int l, float* e, const float* uvab,
   P.e_zero = e_zero; P.agg_mode = agg_mode;
   P.w_row_base = l * 12 * H;
   P.lin_in = st->lin_in; P.lin_out = st->lin_out; P.lin_bias = st->lin_bias; P.lin_rows = st->lin_rows;
-  P.n_tiles = st->lin_out ? 4 * ((st->lin_rows + TC_TILE - 1) / TC_TILE) : (g.E + TC_TILE - 1) / TC_TILE;
+  P.lin_nb = st->lin_nb; P.lin_w_row = st->lin_w_row;
+  P.n_tiles = st->lin_out ? st->lin_nb * ((st->lin_rows + TC_TILE - 1) / TC_TILE) : (g.E + TC_TILE - 1) / TC_TILE;
   if (st->lin_out) P.write_e = 0;
   {
     const char* pe = getenv("DFB_TC_PROBE");
@@ -1094,11 +1099,12 @@ inline int tc_launch_edge_layer(TcState* st, int l, float* e, const float* uvab,
   return 0;
 }
 
-// Node-side linears [rows][256] -> [rows][1024] = U|V|A|B of layer l, on the tensor-core path.
-inline int tc_launch_linear(TcState* st, int l, const float* in, float* out, const float* bias, int rows,
+// Generic [rows][256] x (nb blocks of 256x256, bf16 hi/lo at arena rows w_row + 512 b) -> [rows][nb*256] (+ bias) on the
+// tensor-core path.  nb = 4: the node-side linears U|V|A|B of a layer; nb = 1: node / edge embedding linears.
+inline int tc_launch_linear(TcState* st, int w_row, int nb, const float* in, float* out, const float* bias, int rows,
                             GraphDev g, LayerParams lp, cudaStream_t stream) {
-  st->lin_in = in; st->lin_out = out; st->lin_bias = bias; st->lin_rows = rows;
-  int r = tc_launch_edge_layer(st, l, const_cast<float*>(in), nullptr, nullptr, g, lp, nullptr, 0, 0, nullptr, nullptr,
+  st->lin_in = in; st->lin_out = out; st->lin_bias = bias; st->lin_rows = rows; st->lin_nb = nb; st->lin_w_row = w_row;
+  int r = tc_launch_edge_layer(st, 0, const_cast<float*>(in), nullptr, nullptr, g, lp, nullptr, 0, 0, nullptr, nullptr,
                                AGG_SUM, stream);
   st->lin_in = nullptr; st->lin_out = nullptr; st->lin_bias = nullptr; st->lin_rows = 0;
   return r;
