@@ -6,16 +6,21 @@
 //   e     = e + O silu(LN_O(e_til)) + b_O   (in place)         :449, :339-347
 //
 // Persistent CTAs, one per SM, each looping over 128-edge tiles (edges are row-sorted).
-// Warp roles (192 threads):
-//   warp 0      TMA producer: streams the bf16 hi/lo weight K-chunks (L2 -> smem, 128B swizzle)
-//   warp 1      MMA issuer  : one thread issues tcgen05.mma (M=128, N=256, K=16), owns TMEM alloc
-//   warps 2..5  row workers : thread == edge row == TMEM lane.  They convert the fp32 edge tile to
-//               bf16 hi/lo A-operand chunks, and run the epilogues straight out of TMEM
-//               (a full row lives in one thread, so both LayerNorms need no cross-thread traffic).
+// Warp roles (64 + 128*WPQ threads, WPQ = worker warps per TMEM lane quarter, default 4):
+//   warp 0       TMA producer: streams the bf16 hi/lo weight K-chunks (L2 -> smem, 128B swizzle), L2-prefetches the
+//                next tile's edge rows
+//   warp 1       MMA issuer  : one thread issues tcgen05.mma (M=128, N=256, K=16), owns the TMEM allocation.
+//                GEMM1 takes A from shared memory, GEMM2 takes A from TMEM (written in place by E3)
+//   worker warps thread == edge row == TMEM lane; the 256 channels of a row are split over the WPQ warps of a lane
+//                quarter.  They convert the fp32 edge tile to bf16 hi/lo A chunks and run the epilogues straight out
+//                of TMEM (a row slice lives in one thread: both LayerNorms are thread-local + one smem exchange).
+// Data movement: weights by TMA; gathers of A h[col], V h[col] by coalesced cp.async into swizzled staging; the
+// residual tile in and the result tile out by TMA (no uncoalesced global access on the edge stream).
 // Precision: every 256x256 product is evaluated as  a_hi*b_hi + a_lo*b_hi + a_hi*b_lo  with
 // a = a_hi + a_lo, b = b_hi + b_lo in bf16 and fp32 accumulation in TMEM: ~2^-17 relative error
 // per product, which keeps the 1e-4 fp32 contract (single-pass TF32/BF16 does not: SURVEY D9).
 // The two 128x256 fp32 accumulators (GEMM1, GEMM2) take the full 512 TMEM columns.
+// The same kernel in "linear mode" computes the node-side linears and the embedding linears (GEMM1 + bias only).
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
