@@ -366,6 +366,7 @@ __device__ __forceinline__ void edge_layer_tc_body(const CUtensorMap& wmap, cons
     // ===================================== TMA producer =====================================
     if (lane == 0) {
       uint32_t u = 0, tile_it = 0;
+      const bool tma_in = !P.e_zero && !P.xt_lut;   // residual tile comes from the edge stream (not LUT / zero rows)
       for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++tile_it) {
         // E4 of the previous tile stages its output in A0|A1|B0: do not refill B0 before the store has read it
         if (P.write_e && tile_it > 0) mbar_wait(e4_done, (tile_it - 1) & 1, P.error_flag, 8);
@@ -377,7 +378,17 @@ __device__ __forceinline__ void edge_layer_tc_body(const CUtensorMap& wmap, cons
         for (int i = 0; i < uses_per_tile; ++i, ++u) {
           const int s = u & 1, k = u >> 1, kc = i & 3;
           mbar_wait(&empty[s], (k & 1) ^ 1, P.error_flag, 1);
-          if (Cfg::GATE_B0 && i == 4) mbar_wait(e1_done, tile_it & 1, P.error_flag, 11);
+          if (i == 4) {
+            // every warp has left E1: the A-stage memory (gather buffers) is idle for the rest of the tile (GEMM2 takes
+            // its A operand from TMEM) -> bring in boxes 0..3 of the fp32 residual tile for E4 now; with GATE_B0 this
+            // also releases B0 for GEMM2's first weights
+            mbar_wait(e1_done, tile_it & 1, P.error_flag, 11);
+            if (tma_in) {
+              mbar_arrive_expect_tx(ein_bar, 8 * TC_BOX_BYTES);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) tma_load_2d(smem_base + j * TC_BOX_BYTES, &emap, ein_bar, 32 * j, tile * TC_TILE);
+            }
+          }
           // without GEMM2 (MIS last layer) the next fill of B0 is the NEXT tile's first chunk: same gate, previous tile
           if (Cfg::GATE_B0 && i == 0 && tile_it > 0 && !P.write_e && !P.lin_out && !P.debug_acc)
             mbar_wait(e1_done, (tile_it - 1) & 1, P.error_flag, 12);
@@ -388,6 +399,12 @@ __device__ __forceinline__ void edge_layer_tc_body(const CUtensorMap& wmap, cons
           const int kw = kc;
           tma_load_2d(dst, &wmap, &full_b[s], kw * TC_KCH, rb);
           tma_load_2d(dst + TC_B_BYTES, &wmap, &full_b[s], kw * TC_KCH, rb + 256);
+        }
+        if (P.write_e && tma_in) {
+          // boxes 4..7 of the residual tile land in B0: free once GEMM2's stage-0 MMAs (use 6 of this tile) are done
+          mbar_wait(&empty[0], ((u - 2) >> 1) & 1, P.error_flag, 14);
+#pragma unroll
+          for (int j = 4; j < 8; ++j) tma_load_2d(smem_base + j * TC_BOX_BYTES, &emap, ein_bar, 32 * j, tile * TC_TILE);
         }
       }
     }
@@ -741,7 +758,7 @@ __device__ __forceinline__ void edge_layer_tc_body(const CUtensorMap& wmap, cons
         // every warp must have left E1 before the next tile's setup overwrites s_row / s_col (read by E1's gather
         // setup and segment flush); with GATE_B0 this also marks the gather buffers in B0 dead
         worker_bar();
-        if (Cfg::GATE_B0 && wt == 0) mbar_arrive(e1_done);
+        if (wt == 0) mbar_arrive(e1_done);
         continue;
       }
       tmem_wait_st();
@@ -749,7 +766,8 @@ __device__ __forceinline__ void edge_layer_tc_body(const CUtensorMap& wmap, cons
       // LayerNorm statistics of the column parts are exchanged through the (now idle) per-warp patches:
       // warp (part, q) publishes its 32 rows at patch[0..95] (K,S,Q) and patch[128..191] (S2,Q2)
       if constexpr (WPQ == 1) {
-        worker_bar();   // every warp is done with its gather buffers (stage-A memory) before E3 refills stage A
+        worker_bar();   // every warp is done with its gather buffers
+        if (wt == 0) mbar_arrive(e1_done);
         mean1 = K1 + S1 * (1.0f / H);
         const float var1 = fmaxf(Q1 * (1.0f / H) - (S1 * (1.0f / H)) * (S1 * (1.0f / H)), 0.0f);
         rstd1 = rsqrtf(var1 + LN_EPS);
@@ -758,7 +776,7 @@ __device__ __forceinline__ void edge_layer_tc_body(const CUtensorMap& wmap, cons
         patch[32 + lane] = S1;
         patch[64 + lane] = Q1;
         worker_bar();
-        if (Cfg::GATE_B0 && wt == 0) mbar_arrive(e1_done);   // gather buffers are dead: GEMM2's weights may fill B0
+        if (wt == 0) mbar_arrive(e1_done);   // gather buffers are dead: residual boxes / GEMM2's weights may land
         float kk[WPQ], sp[WPQ], qp[WPQ];
         float msum = 0.f;
 #pragma unroll
@@ -883,16 +901,10 @@ __device__ __forceinline__ void edge_layer_tc_body(const CUtensorMap& wmap, cons
       {
         // All MMAs of the tile are complete: the operand area is idle.  The fp32 residual tile comes in by
         // TMA (8 boxes of [128 rows x 32 cols], 128B swizzle -> conflict-free thread==row access), the result
-        // is written over it and leaves by TMA store: no uncoalesced global access, e read from L2 once more.
+        // (issued by the producer warp while E3 / GEMM2 were still running), the result is written over it and leaves
+        // by TMA store: no uncoalesced global access, e read from L2 once more.
         const bool tma_in = !P.e_zero && !P.xt_lut;
-        if (tma_in) {
-          if (wt == 0) {
-            mbar_arrive_expect_tx(ein_bar, 8 * TC_BOX_BYTES);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) tma_load_2d(smem_base + j * TC_BOX_BYTES, &emap, ein_bar, 32 * j, tile * TC_TILE);
-          }
-          mbar_wait(ein_bar, tile_par, P.error_flag, 10);
-        }
+        if (tma_in) mbar_wait(ein_bar, tile_par, P.error_flag, 10);   // issued early by the producer warp
 #pragma unroll 1
         for (int c0 = cbase; c0 < cbase + Cfg::CPP; c0 += Cfg::CW) {
           uint32_t v[Cfg::CW];
