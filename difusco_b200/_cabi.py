@@ -19,7 +19,7 @@ SYMBOLS = [
     "dfb_set_edge_impl", "dfb_load_weights", "dfb_prepare_graph", "dfb_set_points",
     "dfb_encoder_forward", "dfb_denoise_step", "dfb_denoise", "dfb_denoise_host",
     "dfb_launch_count", "dfb_profile_begin", "dfb_profile_end", "dfb_debug_edge_gemm",
-    "dfb_debug_phase_cycles", "dfb_debug_watchdog",
+    "dfb_debug_phase_cycles", "dfb_debug_watchdog", "dfb_knn_graph",
 ]
 
 _lib = None
@@ -59,6 +59,7 @@ def lib():
   L.dfb_debug_edge_gemm.argtypes = [vp, i32, vp, vp, vp]
   L.dfb_debug_phase_cycles.argtypes = [vp, C.POINTER(C.c_uint64)]
   L.dfb_debug_watchdog.argtypes = [vp, C.POINTER(C.c_int)]
+  L.dfb_knn_graph.argtypes = [vp, vp, i64, i32, i64, vp, vp]
   for name in SYMBOLS:
     fn = getattr(L, name)
     if fn.restype is C.c_int and name not in ("dfb_abi_version",):
@@ -168,6 +169,10 @@ class Context(object):
     self._ck(lib().dfb_denoise_host(self._h, diffusion, points_ptr, edge_index_ptr, num_nodes, num_edges,
                                     gn_segments, xt0_ptr, steps, t1a, ca, la,
                                     int(seed) & 0xFFFFFFFFFFFFFFFF, heatmap_ptr, stream))
+
+  # ---- the step before the path ----
+  def knn_graph(self, points_ptr, num_nodes, k, node_offset, edge_index_ptr, stream=0):
+    self._ck(lib().dfb_knn_graph(self._h, points_ptr, int(num_nodes), int(k), int(node_offset), edge_index_ptr, stream))
 
   # ---- accounting ----
   def launch_count(self):

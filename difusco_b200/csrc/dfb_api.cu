@@ -14,6 +14,7 @@
 #include "edge_layer_fp32.cuh"
 #include "edge_layer_tc.cuh"
 #include "kernels_small.cuh"
+#include "knn.cuh"
 
 using namespace dfb;
 
@@ -860,5 +861,32 @@ extern "C" int dfb_debug_phase_cycles(dfb_ctx* ctx, unsigned long long* out) {
 extern "C" int dfb_debug_watchdog(dfb_ctx* ctx, int* out) {
   if (!ctx || !out || !ctx->tc.error_host) return DFB_E_INVALID;
   for (int i = 0; i < 4; ++i) out[i] = ((volatile int*)ctx->tc.error_host)[i];
+  return DFB_OK;
+}
+
+// ================================================================================================
+// Row f1 (the step before the path): sparse k-NN graph of one TSP instance.
+// Replaces TSPGraphDataset.__getitem__'s KDTree query + edge_index assembly (co_datasets/tsp_graph_dataset.py:52-62).
+//   points      (N,2) float64, HOST or DEVICE (the reference parses coordinates to float64 and queries in float64)
+//   edge_index  (2, N*K) int64, DEVICE: row = arange(N).repeat_interleave(K) (+ node_offset), col = neighbours in
+//               ascending distance (self first) (+ node_offset: block-diagonal batching, pl_meta_model.py:177-184)
+extern "C" int dfb_knn_graph(dfb_ctx* ctx, const double* points, int64_t num_nodes, int k, int64_t node_offset,
+                             int64_t* edge_index, void* stream_) {
+  if (!ctx) return DFB_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream_;
+  CK(ctx, cudaSetDevice(ctx->device));
+  if (num_nodes < 1 || k < 1 || k > num_nodes) FAIL(ctx, DFB_E_INVALID, "bad kNN size N=%lld K=%d", (long long)num_nodes, k);
+  const size_t smem = (size_t)num_nodes * sizeof(double);
+  if (smem > 200 * 1024) FAIL(ctx, DFB_E_UNSUPPORTED, "kNN graph: N=%lld exceeds the shared-memory brute-force limit (25600)", (long long)num_nodes);
+  if (!is_device_ptr(edge_index)) FAIL(ctx, DFB_E_INVALID, "edge_index must be a device pointer");
+  const double* dp = points;
+  if (!is_device_ptr(points)) {
+    ENS(ctx, ctx->d_points, (size_t)num_nodes * 2 * sizeof(double));
+    CK(ctx, cudaMemcpyAsync(ctx->d_points.p, points, (size_t)num_nodes * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+    dp = (const double*)ctx->d_points.p;
+  }
+  CK(ctx, cudaFuncSetAttribute(k_knn_bruteforce, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_knn_bruteforce<<<(int)num_nodes, 256, smem, st>>>(dp, (int)num_nodes, k, (long long*)edge_index, (long long)node_offset);
+  CKL(ctx);
   return DFB_OK;
 }

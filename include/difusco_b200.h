@@ -116,6 +116,13 @@ int dfb_denoise_host(dfb_ctx* ctx, int diffusion_type, const float* points,
                      const float* consts, const int32_t* last_flags, uint64_t seed,
                      float* heatmap_out, void* stream);
 
+/* Row f1 (the step BEFORE the path): sparse k-NN graph of one TSP instance on the GPU.  Replaces the KDTree query +
+ * edge_index assembly of TSPGraphDataset.__getitem__ (co_datasets/tsp_graph_dataset.py:52-62): float64 coordinates
+ * (HOST or DEVICE), neighbours in ascending euclidean distance with self first, edge_index (2, N*k) int64 DEVICE with
+ * row = arange(N).repeat_interleave(k) and both rows shifted by node_offset (block-diagonal batching). */
+int dfb_knn_graph(dfb_ctx* ctx, const double* points, int64_t num_nodes, int k, int64_t node_offset,
+                  int64_t* edge_index, void* stream);
+
 /* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
 int64_t dfb_launch_count(const dfb_ctx* ctx);
 
