@@ -4,18 +4,19 @@
   categorical_denoise_step(xt, t, device, edge_index=None, target_t=None) :118-128
   gaussian_denoise_step(xt, t, device, edge_index=None, target_t=None)    :130-140
   test_step(batch, batch_idx, draw=False, split='test')                   :142-209
-Greedy MIS decoding (mis_decode_np, :194-196) is the next row outside this path (`self.decoder`).
+Greedy MIS decoding (mis_decode_np, :194-196) is `difusco_b200.utils.mis_utils.mis_decode_np`,
+applied by test_step exactly as the reference does (best of all samples -> `{split}/solved_cost`).
 """
 import numpy as np
 import torch
 
 from .pl_meta_model import COMetaModel
+from .utils.mis_utils import mis_decode_np
 
 
 class MISModel(COMetaModel):
   def __init__(self, param_args=None):
     super().__init__(param_args=param_args, node_feature_only=True)
-    self.decoder = None
 
   def forward(self, x, t, edge_index):
     return self.model(x, t, edge_index=edge_index)
@@ -62,11 +63,20 @@ class MISModel(COMetaModel):
       else:
         stacked.append(xt.float().cpu().detach().numpy() + 1e-6)
     predict_labels = np.concatenate(stacked, axis=0)
-    metrics = {f"{split}/predict_labels": predict_labels,
-               f"{split}/gt_cost": node_labels.cpu().numpy().sum()}
-    if self.decoder is not None:
-      metrics.update(self.decoder(predict_labels, base_edge_index.cpu().numpy(),
-                                  self.args.sequential_sampling * P))
+    # decode every sample greedily and keep the largest independent set (pl_mis_model.py:194-209)
+    import scipy.sparse
+    ei_np = base_edge_index.cpu().numpy()
+    adj_mat = scipy.sparse.coo_matrix((np.ones_like(ei_np[0]), (ei_np[0], ei_np[1])))
+    all_sampling = self.args.sequential_sampling * P
+    solved = [mis_decode_np(pl, adj_mat) for pl in np.split(predict_labels, all_sampling)]
+    best_solved_cost = np.max([sol.sum() for sol in solved])
+    gt_cost = node_labels.cpu().numpy().sum()
+    metrics = {f"{split}/gt_cost": gt_cost}
+    for k, v in metrics.items():
+      self.log(k, v, on_epoch=True, sync_dist=True)
+    self.log(f"{split}/solved_cost", best_solved_cost, prog_bar=True, on_epoch=True, sync_dist=True)
+    self.last_predict_labels = predict_labels          # raw heatmaps of the last call (not part of the reference API)
+    self.last_solved_cost = best_solved_cost
     return metrics
 
   def validation_step(self, batch, batch_idx):

@@ -275,6 +275,22 @@ def gen_trajectories():
        meta=np.array([V, 0, 1, steps]))
 
 
+def gen_mis_decode():
+  """utils/mis_utils.py:mis_decode_np of the reference on seeded ER graphs (one case with many exact score ties)."""
+  import scipy.sparse
+  from utils.mis_utils import mis_decode_np as ref_decode
+  out = {}
+  for case, (n, p, seed, ties) in enumerate([(60, 0.1, 1, False), (120, 0.15, 2, False), (80, 0.1, 3, True)]):
+    ei = syn.er_graph_edge_index(n, p, seed, 0)
+    adj = scipy.sparse.coo_matrix((np.ones_like(ei[0]), (ei[0], ei[1])))
+    pred = np.random.default_rng(seed).random(n)
+    if ties:
+      pred = np.round(pred * 4) / 4
+    out[f"ei{case}"], out[f"pred{case}"], out[f"sol{case}"] = ei, pred, ref_decode(pred, adj)
+  save("mis_decode", **out)
+
+
+
 if __name__ == "__main__":
   ap = argparse.ArgumentParser()
   ap.add_argument("--only", default="")
@@ -285,3 +301,5 @@ if __name__ == "__main__":
     gen_forward()
   if a.only in ("", "traj"):
     gen_trajectories()
+  if a.only in ("", "mis_decode"):
+    gen_mis_decode()

@@ -394,3 +394,31 @@ def test_repeated_runs_bitwise_identical(weights2):
   for _ in range(6):
     b = enc2(G.cu(pts), torch.tensor([640.0]), G.cu(xte), G.cu(eit)).cpu().numpy()
     assert np.array_equal(a, b)
+
+
+def test_mis_test_step_end_to_end(weights2):
+  """MISModel.test_step with the reference's batch tuple: denoise loop on the GPU + greedy decode; returns the
+  reference's metrics dict and yields a valid independent set for every parallel sample."""
+  from types import SimpleNamespace as NS
+  from difusco_b200.utils.mis_utils import mis_decode_np
+  import scipy.sparse
+  m = G.mis_model(weights2, "tc", parallel_sampling=2, inference_diffusion_steps=5)
+  ei = syn.er_graph_edge_index(120, 0.1, seed=8, instance=0)
+  labels = torch.zeros(120, dtype=torch.long, device="cuda")
+  graph = NS(x=labels, edge_index=torch.from_numpy(ei).cuda())
+  batch = (torch.tensor([0]), graph, torch.tensor([120], device="cuda"))
+  torch.manual_seed(0)
+  metrics = m.test_step(batch, 0)
+  assert set(metrics) == {"test/gt_cost"} and metrics["test/gt_cost"] == 0
+  pl = m.last_predict_labels
+  assert pl.shape == (240,) and np.isfinite(pl).all()
+  adj = scipy.sparse.coo_matrix((np.ones_like(ei[0]), (ei[0], ei[1]))).tocsr()
+  best = 0
+  for part in np.split(pl, 2):
+    sol = mis_decode_np(part, adj)
+    sel = np.flatnonzero(sol)
+    for i in sel:
+      nb = adj.indices[adj.indptr[i]:adj.indptr[i + 1]]
+      assert not np.any(sol[nb[nb != i]])
+    best = max(best, int(sol.sum()))
+  assert best == m.last_solved_cost and best > 0

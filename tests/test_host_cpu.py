@@ -136,3 +136,20 @@ def test_frequency_tables_are_the_reference_expressions():
   te = orc.timestep_embedding(torch.tensor([517.0]), 256, torch.float32)
   f = torch.from_numpy(t["__const.time_freqs"])
   assert torch.equal(te[0, :128], torch.cos(517.0 * f))
+
+
+def test_mis_decode_matches_reference_function():
+  """utils/mis_utils.py drop-in vs outputs of the reference's mis_decode_np (tests/golden/mis_decode.npz)."""
+  import scipy.sparse
+  from difusco_b200.utils.mis_utils import mis_decode_np
+  g = golden("mis_decode")
+  for case in range(3):
+    ei, pred = g[f"ei{case}"], g[f"pred{case}"]
+    adj = scipy.sparse.coo_matrix((np.ones_like(ei[0]), (ei[0], ei[1])))
+    sol = mis_decode_np(pred, adj)
+    assert np.array_equal(sol, g[f"sol{case}"])
+    sel = np.flatnonzero(sol)                       # independence: no edge between two selected nodes (self loops aside)
+    a = adj.tocsr()
+    for i in sel:
+      nb = a.indices[a.indptr[i]:a.indptr[i + 1]]
+      assert not np.any(sol[nb[nb != i]])
