@@ -20,6 +20,7 @@ SYMBOLS = [
     "dfb_encoder_forward", "dfb_denoise_step", "dfb_denoise", "dfb_denoise_host",
     "dfb_launch_count", "dfb_profile_begin", "dfb_profile_end", "dfb_debug_edge_gemm",
     "dfb_debug_phase_cycles", "dfb_debug_watchdog", "dfb_knn_graph",
+    "dfb_tsp_merge_sparse", "dfb_tsp_merge_order", "dfb_two_opt",
 ]
 
 _lib = None
@@ -60,6 +61,9 @@ def lib():
   L.dfb_debug_phase_cycles.argtypes = [vp, C.POINTER(C.c_uint64)]
   L.dfb_debug_watchdog.argtypes = [vp, C.POINTER(C.c_int)]
   L.dfb_knn_graph.argtypes = [vp, vp, i64, i32, i64, vp, vp]
+  L.dfb_tsp_merge_sparse.argtypes = [vp, i64, vp, vp, i64, i32, vp, C.POINTER(i64)]
+  L.dfb_tsp_merge_order.argtypes = [i64, vp, i64, vp, C.POINTER(i64)]
+  L.dfb_two_opt.argtypes = [vp, vp, i64, vp, i64, i64, C.POINTER(i64), vp]
   for name in SYMBOLS:
     fn = getattr(L, name)
     if fn.restype is C.c_int and name not in ("dfb_abi_version",):
@@ -81,6 +85,37 @@ def _raise(code, msg):
   if code == DFB_E_NOMEM:
     raise MemoryError(msg)
   raise DfbError(msg)
+
+
+MERGE_COMPLETE, MERGE_INCOMPLETE, MERGE_AMBIGUOUS = 0, 1, 2
+
+
+def tsp_merge_sparse(points, heat, edge_index, mode=0):
+  """dfb_tsp_merge_sparse on host arrays -> (status, tour (n+1,) int64, merge_iterations)."""
+  points = np.ascontiguousarray(points, dtype=np.float64)
+  heat = np.ascontiguousarray(heat, dtype=np.float32).reshape(-1)
+  edge_index = np.ascontiguousarray(edge_index, dtype=np.int64)
+  n = points.shape[0]
+  if edge_index.ndim != 2 or edge_index.shape[0] != 2 or edge_index.shape[1] != heat.shape[0]:
+    raise ValueError("edge_index must be (2, E) with one heat value per edge")
+  tour = np.empty(n + 1, dtype=np.int64)
+  it = C.c_int64(0)
+  rc = lib().dfb_tsp_merge_sparse(points.ctypes.data, n, heat.ctypes.data, edge_index.ctypes.data, heat.shape[0],
+                                  int(mode), tour.ctypes.data, C.byref(it))
+  if rc < 0:
+    _raise(rc, "dfb_tsp_merge_sparse: invalid argument (n >= 3, indices inside [0, n), mode 0/1)")
+  return rc, tour, it.value
+
+
+def tsp_merge_order(n, order):
+  """dfb_tsp_merge_order: the reference loop over an explicit order of flattened (i*n + j) entries."""
+  order = np.ascontiguousarray(order, dtype=np.int64).reshape(-1)
+  tour = np.empty(n + 1, dtype=np.int64)
+  it = C.c_int64(0)
+  rc = lib().dfb_tsp_merge_order(int(n), order.ctypes.data, order.shape[0], tour.ctypes.data, C.byref(it))
+  if rc < 0:
+    _raise(rc, "dfb_tsp_merge_order: invalid argument or the order does not complete a tour")
+  return tour, it.value
 
 
 class Context(object):
@@ -171,6 +206,17 @@ class Context(object):
                                     int(seed) & 0xFFFFFFFFFFFFFFFF, heatmap_ptr, stream))
 
   # ---- the step before the path ----
+  def two_opt(self, points, tours, max_iterations, stream=0):
+    """dfb_two_opt on host arrays: returns (tours (B, n+1) int64 copy, iterations)."""
+    points = np.ascontiguousarray(points, dtype=np.float64)
+    tours = np.array(tours, dtype=np.int64, order="C", copy=True)
+    if tours.ndim != 2 or tours.shape[1] != points.shape[0] + 1:
+      raise ValueError("tours must be (batch, n + 1)")
+    it = C.c_int64(0)
+    self._ck(lib().dfb_two_opt(self._h, points.ctypes.data, points.shape[0], tours.ctypes.data, tours.shape[0],
+                               int(max_iterations), C.byref(it), stream))
+    return tours, it.value
+
   def knn_graph(self, points_ptr, num_nodes, k, node_offset, edge_index_ptr, stream=0):
     self._ck(lib().dfb_knn_graph(self._h, points_ptr, int(num_nodes), int(k), int(node_offset), edge_index_ptr, stream))
 

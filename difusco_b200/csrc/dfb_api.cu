@@ -15,6 +15,7 @@
 #include "edge_layer_tc.cuh"
 #include "kernels_small.cuh"
 #include "knn.cuh"
+#include "tsp_decode.cuh"
 
 using namespace dfb;
 
@@ -47,6 +48,7 @@ struct dfb_ctx {
   DevBuf d_row, d_col, d_perm, d_rowptr, d_grp_first, d_grp_pair, d_ei_stage;
   // ---- workspace ----
   DevBuf e, h, h0, uvab, uvab0, partials, feat, tvec, tvals, gn_part, gn_stats, d_points, d_xt, d_u;
+  DevBuf opt_points, opt_tours, opt_pos, opt_dnext, opt_cand, opt_tiles, opt_state;   // 2-opt (row f3)
   int tvec_steps_cap = 0;
   // ---- accounting ----
   int64_t launches = 0;
@@ -888,5 +890,76 @@ extern "C" int dfb_knn_graph(dfb_ctx* ctx, const double* points, int64_t num_nod
   CK(ctx, cudaFuncSetAttribute(k_knn_bruteforce, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_knn_bruteforce<<<(int)num_nodes, 256, smem, st>>>(dp, (int)num_nodes, k, (long long*)edge_index, (long long)node_offset);
   CKL(ctx);
+  return DFB_OK;
+}
+
+// ================================================================================================
+// Rows f2 / f3 (the steps after the path): tour merge on the host, 2-opt on the GPU.  See tsp_decode.cuh.
+extern "C" int dfb_tsp_merge_sparse(const double* points, int64_t n, const float* heat, const int64_t* edge_index, int64_t E,
+                                    int mode, int64_t* tour, int64_t* merge_iterations) {
+  if (!points || !heat || !edge_index || !tour || !merge_iterations || n < 3 || n > 0x7fffffff / 2 || E < 0 || (mode != 0 && mode != 1))
+    return DFB_E_INVALID;
+  int r = tspmerge::merge_sparse(points, (int)n, heat, edge_index, E, mode, tour, merge_iterations);
+  return r < 0 ? DFB_E_INVALID : r;
+}
+
+extern "C" int dfb_tsp_merge_order(int64_t n, const int64_t* order, int64_t count, int64_t* tour, int64_t* merge_iterations) {
+  if (!order || !tour || !merge_iterations || n < 3 || n > 0x7fffffff / 2 || count < 0) return DFB_E_INVALID;
+  int r = tspmerge::merge_order((int)n, order, count, tour, merge_iterations);
+  return r < 0 ? DFB_E_INVALID : r;
+}
+
+extern "C" int dfb_two_opt(dfb_ctx* ctx, const double* points, int64_t n, int64_t* tours, int64_t batch, int64_t max_iterations,
+                           int64_t* iterations_out, void* stream_) {
+  if (!ctx) return DFB_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream_;
+  CK(ctx, cudaSetDevice(ctx->device));
+  if (!points || !tours || !iterations_out) FAIL(ctx, DFB_E_INVALID, "two_opt: null argument");
+  if (n < 3 || n > 46340 || batch < 1 || batch > 64) FAIL(ctx, DFB_E_INVALID, "two_opt: bad size n=%lld batch=%lld (n in [3, 46340], batch in [1, 64])", (long long)n, (long long)batch);
+  const int N = (int)n, B = (int)batch;
+  for (int64_t k = 0; k < batch * (n + 1); ++k)
+    if (tours[k] < 0 || tours[k] >= n) FAIL(ctx, DFB_E_INVALID, "two_opt: tour entry %lld out of range", (long long)tours[k]);
+  const int T = (N + TWOOPT_TILE - 1) / TWOOPT_TILE;
+  std::vector<int2> tiles;
+  for (int a = 0; a < T; ++a)
+    for (int b = a; b < T; ++b) tiles.push_back(make_int2(a, b));
+  const int ntiles = (int)tiles.size();
+  ENS(ctx, ctx->opt_points, (size_t)N * 2 * sizeof(double));
+  ENS(ctx, ctx->opt_tours, (size_t)B * (N + 1) * sizeof(long long));
+  ENS(ctx, ctx->opt_pos, (size_t)B * (N + 1) * 2 * sizeof(double));
+  ENS(ctx, ctx->opt_dnext, (size_t)B * N * sizeof(double));
+  ENS(ctx, ctx->opt_cand, (size_t)B * ntiles * sizeof(TwoOptCand));
+  ENS(ctx, ctx->opt_tiles, (size_t)ntiles * sizeof(int2));
+  ENS(ctx, ctx->opt_state, sizeof(TwoOptState));
+  double* d_points = (double*)ctx->opt_points.p;
+  long long* d_tours = (long long*)ctx->opt_tours.p;
+  double* d_pos = (double*)ctx->opt_pos.p;
+  double* d_dnext = (double*)ctx->opt_dnext.p;
+  TwoOptCand* d_cand = (TwoOptCand*)ctx->opt_cand.p;
+  int2* d_tiles = (int2*)ctx->opt_tiles.p;
+  TwoOptState* d_state = (TwoOptState*)ctx->opt_state.p;
+  CK(ctx, cudaMemcpyAsync(d_points, points, (size_t)N * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+  CK(ctx, cudaMemcpyAsync(d_tours, tours, (size_t)B * (N + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
+  CK(ctx, cudaMemcpyAsync(d_tiles, tiles.data(), (size_t)ntiles * sizeof(int2), cudaMemcpyHostToDevice, st));
+  CK(ctx, cudaMemsetAsync(d_state, 0, sizeof(TwoOptState), st));
+  k_twoopt_init<<<dim3((N + 256) / 256, B), 256, 0, st>>>(d_points, d_tours, d_pos, d_dnext, N);
+  CKL(ctx);
+  TwoOptState hs{};
+  int chunk = 8;
+  while (true) {
+    for (int c = 0; c < chunk; ++c) {
+      k_twoopt_eval<<<dim3(ntiles, B), 256, 0, st>>>(d_pos, d_dnext, d_tiles, d_cand, d_state, N, ntiles);
+      CKL(ctx);
+      k_twoopt_apply<<<1, 1024, 0, st>>>(d_tours, d_pos, d_dnext, d_cand, d_state, N, B, ntiles, (long long)max_iterations);
+      CKL(ctx);
+    }
+    CK(ctx, cudaMemcpyAsync(&hs, d_state, sizeof(hs), cudaMemcpyDeviceToHost, st));
+    CK(ctx, cudaStreamSynchronize(st));
+    if (hs.done) break;
+    if (chunk < 64) chunk *= 2;
+  }
+  CK(ctx, cudaMemcpyAsync(tours, d_tours, (size_t)B * (N + 1) * sizeof(long long), cudaMemcpyDeviceToHost, st));
+  CK(ctx, cudaStreamSynchronize(st));
+  *iterations_out = hs.iterations;
   return DFB_OK;
 }

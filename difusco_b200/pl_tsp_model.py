@@ -5,20 +5,22 @@ Same method names and signatures on the denoise path:
   categorical_denoise_step(points, xt, t, device, edge_index=None, target_t=None)   :122-138
   gaussian_denoise_step(points, xt, t, device, edge_index=None, target_t=None)      :140-151
   test_step(batch, batch_idx, split='test')                                   :153-256
-test_step runs the reference's loop (:185-222) as ONE fused device loop and returns the heatmap;
-tour decoding (merge_tours / 2-opt, :227-237) is the next row outside this path: plug a callable
-into `self.decoder(adj_mat, np_points, np_edge_index) -> dict` to get solved-cost metrics.
+test_step runs the reference's loop (:185-222) as ONE fused device loop, then the reference's decode
+(:227-256): merge_tours (host C++), batched 2-opt (CUDA), TSPEvaluator - and returns the
+reference's metrics dict.  `--save_numpy_heatmap` (:224-225, :258-267) is honoured.
 """
+import os
+
 import numpy as np
 import torch
 
 from .pl_meta_model import COMetaModel
+from .utils.tsp_utils import TSPEvaluator, batched_two_opt_torch, merge_tours
 
 
 class TSPModel(COMetaModel):
   def __init__(self, param_args=None):
     super().__init__(param_args=param_args, node_feature_only=False)
-    self.decoder = None
 
   def forward(self, x, adj, t, edge_index):
     return self.model(x, t, adj, edge_index)
@@ -83,7 +85,9 @@ class TSPModel(COMetaModel):
       else:
         points = points.repeat(P, 1)
         edge_index = self.duplicate_edge_index(edge_index, np_points.shape[0], device)
-    heatmaps = []
+    np_gt_tour = gt_tour.cpu().numpy().reshape(-1)
+    stacked_tours, heatmaps = [], []
+    ns, merge_iterations = 0, 0
     for _ in range(self.args.sequential_sampling):
       xt = torch.randn_like(adj_matrix.float())
       if P > 1:
@@ -99,10 +103,45 @@ class TSPModel(COMetaModel):
       else:
         adj_mat = xt.float().cpu().detach().numpy() + 1e-6
       heatmaps.append(adj_mat)
-    metrics = {f"{split}/heatmap": heatmaps[-1] if len(heatmaps) == 1 else np.stack(heatmaps)}
-    if self.decoder is not None:
-      metrics.update(self.decoder(heatmaps, np_points, np_edge_index, gt_tour))
+      if getattr(self.args, "save_numpy_heatmap", False):
+        self.run_save_numpy_heatmap(adj_mat, np_points, real_batch_idx, split)
+      tours, merge_iterations = merge_tours(adj_mat, np_points, np_edge_index, sparse_graph=self.sparse,
+                                            parallel_sampling=P,
+                                            exact=getattr(self.args, "exact_merge", True))
+      solved_tours, ns = batched_two_opt_torch(np_points.astype("float64"), np.array(tours).astype("int64"),
+                                               max_iterations=getattr(self.args, "two_opt_iterations", 1000),
+                                               device=device)
+      stacked_tours.append(solved_tours)
+    solved_tours = np.concatenate(stacked_tours, axis=0)
+    tsp_solver = TSPEvaluator(np_points)
+    gt_cost = tsp_solver.evaluate(np_gt_tour)
+    all_solved_costs = [tsp_solver.evaluate(solved_tours[i]) for i in range(P * self.args.sequential_sampling)]
+    best_solved_cost = np.min(all_solved_costs)
+    metrics = {f"{split}/gt_cost": gt_cost, f"{split}/2opt_iterations": ns,
+               f"{split}/merge_iterations": merge_iterations}
+    for k, v in metrics.items():
+      self.log(k, v, on_epoch=True, sync_dist=True)
+    self.log(f"{split}/solved_cost", best_solved_cost, prog_bar=True, on_epoch=True, sync_dist=True)
+    # not part of the reference's return value: kept for callers that want the artefacts of the last call
+    self.last_heatmap = heatmaps[-1] if len(heatmaps) == 1 else np.stack(heatmaps)
+    self.last_solved_tours, self.last_solved_cost = solved_tours, best_solved_cost
     return metrics
+
+  def run_save_numpy_heatmap(self, adj_mat, np_points, real_batch_idx, split):
+    """--save_numpy_heatmap (pl_tsp_model.py:258-267): <save_dir>/<name>/<version>/numpy_heatmap/{split}-heatmap-<idx>.npy
+    and {split}-points-<idx>.npy, the input format of tsp_mcts/convert_numpy_to_txt.py."""
+    if self.args.parallel_sampling > 1 or self.args.sequential_sampling > 1:
+      raise NotImplementedError("Save numpy heatmap only support single sampling")
+    logger = getattr(self, "logger", None)
+    if logger is not None:
+      exp_save_dir = os.path.join(logger.save_dir, logger.name, logger.version)
+    else:
+      exp_save_dir = getattr(self.args, "storage_path", ".")
+    heatmap_path = os.path.join(exp_save_dir, "numpy_heatmap")
+    os.makedirs(heatmap_path, exist_ok=True)
+    real_batch_idx = real_batch_idx.cpu().numpy().reshape(-1)[0]
+    np.save(os.path.join(heatmap_path, f"{split}-heatmap-{real_batch_idx}.npy"), adj_mat)
+    np.save(os.path.join(heatmap_path, f"{split}-points-{real_batch_idx}.npy"), np_points)
 
   def validation_step(self, batch, batch_idx):
     return self.test_step(batch, batch_idx, split="val")

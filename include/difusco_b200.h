@@ -123,6 +123,28 @@ int dfb_denoise_host(dfb_ctx* ctx, int diffusion_type, const float* points,
 int dfb_knn_graph(dfb_ctx* ctx, const double* points, int64_t num_nodes, int k, int64_t node_offset,
                   int64_t* edge_index, void* stream);
 
+/* Row f2 (the step AFTER the path): greedy edge-insertion tour merge, utils/tsp_utils.py:89-145 with
+ * utils/cython_merge/cython_merge.pyx:19-120.  HOST code, HOST pointers, no context.
+ *   points (n,2) float64; heat (E,) float32 over edge_index (2,E) int64 (the dense case passes the row-major complete
+ *   graph with heat = adj.flatten()); tour (n+1,) int64 out; merge_iterations out (the reference's counter).
+ * Only the non-zero heat entries are sorted instead of the reference's dense n*n argsort.
+ *   mode 0: returns 0 when the tour completes inside them (identical to the reference), 1 when it does not (the rest
+ *           of the reference's order is a tie at key 0 whose order is numpy's argsort artefact: the caller then runs
+ *           dfb_tsp_merge_order on that argsort), 2 when two different pairs tie exactly (same fallback).
+ *   mode 1: never falls back; leftover fragment ends are joined by increasing distance (NOT the reference's result
+ *           once the non-zero entries run out; opt-in for large n).
+ * Negative return: DFB_E_INVALID. */
+int dfb_tsp_merge_sparse(const double* points, int64_t n, const float* heat, const int64_t* edge_index, int64_t E,
+                         int mode, int64_t* tour, int64_t* merge_iterations);
+/* The reference loop over an explicit visiting order of the flattened n*n entries (cython_merge.pyx:44-98). */
+int dfb_tsp_merge_order(int64_t n, const int64_t* order, int64_t count, int64_t* tour, int64_t* merge_iterations);
+
+/* Row f3: batched 2-opt, utils/tsp_utils.py:12-49 (batched_two_opt_torch).  points (n,2) float64 HOST, tours
+ * (batch, n+1) int64 HOST, updated in place; iterations_out = the reference's `iterator`.  Same moves in the same
+ * order as the reference on its CPU device (float64, first-occurrence arg-min, batch-wide stopping rule). */
+int dfb_two_opt(dfb_ctx* ctx, const double* points, int64_t n, int64_t* tours, int64_t batch, int64_t max_iterations,
+                int64_t* iterations_out, void* stream);
+
 /* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
 int64_t dfb_launch_count(const dfb_ctx* ctx);
 

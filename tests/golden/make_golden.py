@@ -291,6 +291,87 @@ def gen_mis_decode():
 
 
 
+def _reference_tsp_utils():
+  """The reference's utils/tsp_utils.py with its real Cython merge: the .pyx is compiled from where it lies in
+  /root/reference into a scratch directory under /tmp (nothing is copied into this repository)."""
+  import importlib, subprocess, tempfile, shutil
+  build = os.path.join(tempfile.gettempdir(), "dfb_ref_cython_merge")
+  os.makedirs(build, exist_ok=True)
+  if not any(f.startswith("cython_merge.") and f.endswith(".so") for f in os.listdir(build)):
+    shutil.copy(os.path.join(ref_shims.REFERENCE_ROOT, "utils", "cython_merge", "cython_merge.pyx"), build)
+    with open(os.path.join(build, "setup.py"), "w") as f:
+      f.write("from setuptools import setup, Extension\nfrom Cython.Build import cythonize\nimport numpy\n"
+              "setup(ext_modules=cythonize([Extension('cython_merge', ['cython_merge.pyx'], "
+              "include_dirs=[numpy.get_include()])], language_level=3))\n")
+    subprocess.run([sys.executable, "setup.py", "build_ext", "--inplace"], cwd=build, check=True,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+  sys.path.insert(0, build)
+  real = importlib.import_module("cython_merge")
+  import utils.tsp_utils as tu
+  tu.merge_cython = real.merge_cython
+  return tu
+
+
+def tsp_decode_cases():
+  """(name, N, K (0 = dense), P, heat kind) of the decode fixtures; shared with the tests."""
+  return [("s50", 50, 8, 1, "good"), ("s200", 200, 10, 2, "noisy"), ("s120r", 120, 5, 1, "random"),
+          ("s300g", 300, 12, 1, "gauss"), ("s30full", 30, 30, 2, "noisy"), ("s40fullg", 40, 40, 1, "gauss"), ("d20", 20, 0, 2, "noisy"), ("d45", 45, 0, 1, "good")]
+
+
+def tsp_decode_inputs(name, n, k, par, kind):
+  """Synthetic heatmaps with the layout test_step hands to merge_tours (pl_tsp_model.py:218-231): sparse ->
+  (P*E,) float32 over the kNN edge list; dense -> (P, N, N) float32."""
+  rng = np.random.default_rng(sum(map(ord, name)))
+  pts = syn.tsp_points(n, seed=7 + n, instance=0).astype(np.float32)
+  if k:
+    ei = syn.knn_edge_index(pts, k)
+    d = np.linalg.norm(pts[ei[0]] - pts[ei[1]], axis=-1)
+    shape = (par * ei.shape[1],)
+    d = np.tile(d, par)
+  else:
+    ei = None
+    d = np.linalg.norm(pts[:, None] - pts[None], axis=-1)
+    shape = (par, n, n)
+    d = np.broadcast_to(d, shape)
+  u = rng.random(shape)
+  if kind == "good":
+    heat = np.exp(-8.0 * d * np.sqrt(n)) * (0.7 + 0.3 * u) + 1e-6
+  elif kind == "noisy":
+    heat = np.exp(-3.0 * d * np.sqrt(n)) * u + 1e-6
+  elif kind == "random":
+    heat = u + 1e-6
+  else:                      # gaussian-diffusion style output: xt * 0.5 + 0.5 may leave [0, 1]
+    heat = (np.exp(-6.0 * d * np.sqrt(n)) * 2 - 1 + 0.4 * rng.standard_normal(shape)) * 0.5 + 0.5
+  return pts, ei, heat.astype(np.float32)
+
+
+def gen_tsp_decode():
+  """utils/tsp_utils.py of the reference: merge_tours (with the real Cython merge), batched_two_opt_torch on
+  the CPU device, TSPEvaluator."""
+  tu = _reference_tsp_utils()
+  out = {}
+  for name, n, k, par, kind in tsp_decode_cases():
+    pts, ei, heat = tsp_decode_inputs(name, n, k, par, kind)
+    import warnings
+    with warnings.catch_warnings():
+      warnings.simplefilter("ignore")
+      tours, merge_it = tu.merge_tours(heat, pts, ei, sparse_graph=bool(k), parallel_sampling=par)
+    tours = np.array(tours).astype("int64")
+    out[f"{name}/points"], out[f"{name}/heat"] = pts, heat
+    if k:
+      out[f"{name}/edge_index"] = ei
+    out[f"{name}/tours"], out[f"{name}/merge_iterations"] = tours, np.float64(merge_it)
+    for cap in (3, 1000):
+      solved, ns = tu.batched_two_opt_torch(pts.astype("float64"), tours, max_iterations=cap, device="cpu")
+      out[f"{name}/two_opt_{cap}"], out[f"{name}/two_opt_{cap}_iters"] = solved, np.int64(ns)
+    ev = tu.TSPEvaluator(pts)
+    out[f"{name}/cost_merged"] = np.array([ev.evaluate(t) for t in tours])
+    out[f"{name}/cost_solved"] = np.array([ev.evaluate(t) for t in out[f"{name}/two_opt_1000"]])
+    print(name, "merge_it", merge_it, "2opt", int(out[f"{name}/two_opt_1000_iters"]),
+          out[f"{name}/cost_merged"], out[f"{name}/cost_solved"])
+  save("tsp_decode", **out)
+
+
 if __name__ == "__main__":
   ap = argparse.ArgumentParser()
   ap.add_argument("--only", default="")
@@ -303,3 +384,5 @@ if __name__ == "__main__":
     gen_trajectories()
   if a.only in ("", "mis_decode"):
     gen_mis_decode()
+  if a.only in ("", "tsp_decode"):
+    gen_tsp_decode()

@@ -1,0 +1,230 @@
+"""tour merge (host C++), 2-opt (CUDA) and the evaluator against the reference's outputs
+(tests/golden/tsp_decode.npz, produced by the reference's own merge_tours / batched_two_opt_torch / TSPEvaluator)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+
+from difusco_b200 import _cabi
+from difusco_b200.utils import tsp_utils as tu
+from oracle import tsp_decode_oracle as orc
+from conftest import golden as _load_golden
+
+# name, K (0 = dense input), parallel_sampling
+CASES = [("s50", 8, 1), ("s200", 10, 2), ("s120r", 5, 1), ("s300g", 12, 1), ("s30full", 30, 2), ("s40fullg", 40, 1),
+         ("d20", 0, 2), ("d45", 0, 1)]
+
+
+def load(name, k):
+  g = _load_golden("tsp_decode")
+  return g, g[f"{name}/points"], g[f"{name}/heat"], (g[f"{name}/edge_index"] if k else None)
+
+
+def is_tour(t, n):
+  return len(t) == n + 1 and t[0] == t[-1] == 0 and sorted(t[:-1]) == list(range(n))
+
+
+@pytest.mark.parametrize("name,k,par", CASES)
+def test_merge_tours_matches_reference(name, k, par):
+  g, pts, heat, ei = load(name, k)
+  tours, it = tu.merge_tours(heat, pts, ei, sparse_graph=bool(k), parallel_sampling=par)
+  assert np.array_equal(np.array(tours), g[f"{name}/tours"])
+  assert it == float(g[f"{name}/merge_iterations"])
+
+
+@pytest.mark.parametrize("name,k,par", [c for c in CASES if c[0] in ("s50", "s30full", "s40fullg", "d20")])
+def test_merge_oracle_matches_reference(name, k, par):
+  g, pts, heat, ei = load(name, k)
+  for p, part in enumerate(np.split(heat, par, axis=0)):
+    sym = orc.symmetric_heat(len(pts), part if k else part[0], ei)
+    tour, it = orc.greedy_merge(pts, sym)
+    assert np.array_equal(tour, g[f"{name}/tours"][p])
+  # merge_iterations is the mean over the parallel samples; check it on the single-sample cases
+  if par == 1:
+    assert it == float(g[f"{name}/merge_iterations"])
+
+
+def test_merge_fast_path_needs_no_dense_order():
+  """Tours that close inside the non-zero entries come from the sparse scan alone (status 0), counter included."""
+  g, pts, heat, ei = load("s30full", 30)
+  for p, part in enumerate(np.split(heat, 2)):
+    status, tour, it = _cabi.tsp_merge_sparse(pts, part, ei, mode=0)
+    assert status == _cabi.MERGE_COMPLETE
+    assert np.array_equal(tour, g["s30full/tours"][p])
+  g, pts, heat, ei = load("s50", 8)
+  assert _cabi.tsp_merge_sparse(pts, heat, ei, mode=0)[0] == _cabi.MERGE_INCOMPLETE
+
+
+@pytest.mark.parametrize("name,k,par", CASES)
+def test_merge_distance_completion_gives_valid_tours(name, k, par):
+  g, pts, heat, ei = load(name, k)
+  tours, _ = tu.merge_tours(heat, pts, ei, sparse_graph=bool(k), parallel_sampling=par, exact=False)
+  ev = tu.TSPEvaluator(pts)
+  for p, t in enumerate(tours):
+    assert is_tour(t, len(pts))
+    if not k or name.endswith("full") or name.endswith("fullg"):     # closes inside the candidates: same as exact
+      assert np.array_equal(t, g[f"{name}/tours"][p])
+    else:                                                             # nearest-end completion beats arbitrary ties
+      assert ev.evaluate(t) <= g[f"{name}/cost_merged"][p] + 1e-9
+
+
+def test_merge_exact_key_tie_falls_back_to_reference_order():
+  """Two different pairs with bit-identical keys: the scan reports it and merge_tours resolves it like the reference
+  (through the argsort); the oracle does the same argsort, so both agree."""
+  pts = np.array([[0, 0], [1, 0], [1, 1], [0, 1], [0.5, 2.0]], dtype=np.float32)
+  ei = np.array([[0, 1, 2, 3, 0, 1, 2], [1, 2, 3, 0, 4, 4, 4]], dtype=np.int64)
+  heat = np.array([0.5, 0.5, 0.5, 0.5, 0.1, 0.2, 0.3], dtype=np.float32)
+  assert _cabi.tsp_merge_sparse(pts, heat, ei, mode=0)[0] == _cabi.MERGE_AMBIGUOUS
+  tours, it = tu.merge_tours(heat, pts, ei, sparse_graph=True)
+  tour, it_o = orc.greedy_merge(pts, orc.symmetric_heat(5, heat, ei))
+  assert tours[0] == list(tour) and it == it_o
+
+
+def test_merge_argument_errors():
+  pts = np.zeros((4, 2))
+  with pytest.raises(ValueError):
+    _cabi.tsp_merge_sparse(pts, np.ones(2, np.float32), np.array([[0, 9], [1, 2]]))       # node index out of range
+  with pytest.raises(ValueError):
+    _cabi.tsp_merge_sparse(pts[:2], np.ones(1, np.float32), np.array([[0], [1]]))          # n < 3
+  with pytest.raises(ValueError):
+    _cabi.tsp_merge_sparse(pts, np.ones(3, np.float32), np.array([[0, 1], [1, 2]]))        # heat / edge mismatch
+  with pytest.raises(ValueError):
+    _cabi.tsp_merge_order(4, np.array([1]))                                                # order cannot finish a tour
+
+
+@pytest.mark.parametrize("name,k,par", CASES)
+def test_evaluator_matches_reference(name, k, par):
+  g, pts, _, _ = load(name, k)
+  ev = tu.TSPEvaluator(pts)
+  for p in range(par):
+    assert ev.evaluate(g[f"{name}/tours"][p]) == g[f"{name}/cost_merged"][p]
+    assert ev.evaluate(g[f"{name}/two_opt_1000"][p]) == g[f"{name}/cost_solved"][p]
+    assert orc.tour_length(pts, g[f"{name}/tours"][p]) == g[f"{name}/cost_merged"][p]
+
+
+@pytest.mark.parametrize("name,k,par", [c for c in CASES if c[0] in ("s50", "s200", "d20")])
+def test_two_opt_oracle_matches_reference(name, k, par):
+  g, pts, _, _ = load(name, k)
+  for cap in (3, 1000):
+    solved, ns = orc.two_opt(pts, g[f"{name}/tours"], cap)
+    assert np.array_equal(solved, g[f"{name}/two_opt_{cap}"]) and ns == int(g[f"{name}/two_opt_{cap}_iters"])
+
+
+def test_two_opt_requires_cuda_device():
+  with pytest.raises(RuntimeError):
+    tu.batched_two_opt_torch(np.zeros((4, 2)), np.array([[0, 1, 2, 3, 0]]), device="cpu")
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,k,par", CASES)
+def test_two_opt_matches_reference(name, k, par):
+  g, pts, _, _ = load(name, k)
+  for cap in (3, 1000):
+    solved, ns = tu.batched_two_opt_torch(pts.astype("float64"), g[f"{name}/tours"], max_iterations=cap, device="cuda")
+    assert ns == int(g[f"{name}/two_opt_{cap}_iters"])
+    assert np.array_equal(solved, g[f"{name}/two_opt_{cap}"])
+
+
+@pytest.mark.gpu
+def test_two_opt_matches_oracle_on_random_tours():
+  """Random permutations (many improving moves, several tiles per row, batch-wide stopping rule with B = 3)."""
+  rng = np.random.default_rng(5)
+  n = 150
+  pts = rng.random((n, 2)).astype(np.float32)
+  tours = np.stack([np.concatenate([[0], 1 + rng.permutation(n - 1), [0]]) for _ in range(3)]).astype(np.int64)
+  for cap in (1, 40, 5000):
+    want, ns_want = orc.two_opt(pts, tours, cap)
+    got, ns = tu.batched_two_opt_torch(pts.astype("float64"), tours, max_iterations=cap, device="cuda")
+    assert ns == ns_want and np.array_equal(got, want)
+
+
+@pytest.mark.gpu
+def test_two_opt_large_instance_properties():
+  """TSP-2000 (beyond what the oracle finishes quickly): result is a permutation, never longer than the input,
+  locally optimal when it stops by itself, and the iteration cap is honoured."""
+  rng = np.random.default_rng(6)
+  n = 2000
+  pts = rng.random((n, 2))
+  order = np.argsort(pts[:, 0] + 0.05 * rng.random(n))              # a crude but not random start
+  order = np.concatenate([[0], order[order != 0], [0]])
+  tours = np.stack([order, order]).astype(np.int64)
+  ev = tu.TSPEvaluator(pts)
+  capped, ns = tu.batched_two_opt_torch(pts, tours, max_iterations=25, device="cuda")
+  assert ns == 25 and is_tour(list(capped[0]), n) and ev.evaluate(capped[0]) < ev.evaluate(tours[0])
+  assert np.array_equal(capped[0], capped[1])
+  solved, ns = tu.batched_two_opt_torch(pts, tours, max_iterations=100000, device="cuda")
+  assert is_tour(list(solved[0]), n) and ev.evaluate(solved[0]) < ev.evaluate(capped[0])
+  again, ns2 = tu.batched_two_opt_torch(pts, solved, max_iterations=100000, device="cuda")
+  assert ns2 == 0 and np.array_equal(again, solved)
+
+
+@pytest.mark.gpu
+def test_two_opt_argument_errors():
+  with pytest.raises(ValueError):
+    tu.batched_two_opt_torch(np.zeros((4, 2)), np.array([[0, 1, 2, 7, 0]]), device="cuda")
+  with pytest.raises(ValueError):
+    tu.batched_two_opt_torch(np.zeros((4, 2)), np.array([[0, 1, 2, 0]]), device="cuda")
+
+
+def _dataset_file(tmp, n, count, seed):
+  rng = np.random.default_rng(seed)
+  f = os.path.join(tmp, "tsp.txt")
+  with open(f, "w") as fh:
+    for _ in range(count):
+      p = rng.random((n, 2))
+      t = np.r_[0, 1 + rng.permutation(n - 1), 0]
+      fh.write(" ".join(f"{float(x)!r} {float(y)!r}" for x, y in p) + " output " + " ".join(str(i + 1) for i in t) + "\n")
+  return f
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sparse_factor,par,dtype", [(10, 2, "categorical"), (12, 1, "gaussian"), (-1, 2, "categorical")])
+def test_tsp_test_step_end_to_end(sparse_factor, par, dtype, tmp_path):
+  """TSPModel.test_step on a batch built like the reference's DataLoader builds it: dataset mirror (GPU kNN) ->
+  fused denoise loop -> merge -> 2-opt -> evaluator.  Metrics keys are the reference's; every number is re-derived
+  from the artefacts through the oracle."""
+  import torch
+  from types import SimpleNamespace as NS
+  import gpu_util as G
+  from difusco_b200 import synthetic as syn
+  from difusco_b200.co_datasets.tsp_graph_dataset import TSPGraphDataset
+  n = 60
+  ds = TSPGraphDataset(_dataset_file(str(tmp_path), n, 2, 3), sparse_factor=sparse_factor)
+  oc = 1 if dtype == "gaussian" else 2
+  m = G.tsp_model(syn.make_encoder_weights(seed=oc, out_channels=oc), "tc", sparse_factor=sparse_factor,
+                  parallel_sampling=par, diffusion_type=dtype, inference_diffusion_steps=4, two_opt_iterations=50,
+                  save_numpy_heatmap=(par == 1), storage_path=str(tmp_path))
+  item = ds[1]
+  if sparse_factor > 0:
+    idx, graph, pi, ei_ind, tour = item
+    graph = NS(x=graph.x.cuda(), edge_index=graph.edge_index.cuda(), edge_attr=graph.edge_attr.cuda())
+    batch = (idx.reshape(1, 1), graph, pi.reshape(1, 1).cuda(), ei_ind.reshape(1, 1).cuda(), tour.reshape(1, -1).cuda())
+    pts, ei = graph.x.cpu().numpy(), graph.edge_index.cpu().numpy()
+  else:
+    idx, p, adj, tour = item
+    batch = (idx.reshape(1, 1), p[None].cuda(), adj[None].cuda(), tour.reshape(1, -1).cuda())
+    pts, ei = p.numpy(), None
+  torch.manual_seed(1)
+  metrics = m.test_step(batch, 0)
+  assert set(metrics) == {"test/gt_cost", "test/2opt_iterations", "test/merge_iterations"}
+  assert metrics["test/gt_cost"] == orc.tour_length(pts, tour.numpy().reshape(-1))
+  heat = m.last_heatmap
+  want_tours, its = [], []
+  for part in np.split(heat, par, axis=0):
+    t, it = orc.greedy_merge(pts, orc.symmetric_heat(n, part if ei is not None else part[0], ei))
+    want_tours.append(t)
+    its.append(it)
+  assert metrics["test/merge_iterations"] == np.mean(its)
+  solved, ns = orc.two_opt(pts, np.array(want_tours), 50)
+  assert metrics["test/2opt_iterations"] == ns and np.array_equal(solved, m.last_solved_tours)
+  assert m.last_solved_cost == min(orc.tour_length(pts, t) for t in solved)
+  if par == 1:
+    saved = np.load(os.path.join(str(tmp_path), "numpy_heatmap", "test-heatmap-1.npy"))
+    assert np.array_equal(saved, heat)
+    assert np.array_equal(np.load(os.path.join(str(tmp_path), "numpy_heatmap", "test-points-1.npy")), pts)
