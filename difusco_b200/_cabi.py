@@ -20,7 +20,7 @@ SYMBOLS = [
     "dfb_encoder_forward", "dfb_denoise_step", "dfb_denoise", "dfb_denoise_host",
     "dfb_launch_count", "dfb_profile_begin", "dfb_profile_end", "dfb_debug_edge_gemm",
     "dfb_debug_phase_cycles", "dfb_debug_watchdog", "dfb_knn_graph",
-    "dfb_tsp_merge_sparse", "dfb_tsp_merge_order", "dfb_two_opt",
+    "dfb_tsp_merge_sparse", "dfb_tsp_merge_order", "dfb_two_opt", "dfb_write_heatmap_txt",
 ]
 
 _lib = None
@@ -64,6 +64,7 @@ def lib():
   L.dfb_tsp_merge_sparse.argtypes = [vp, i64, vp, vp, i64, i32, vp, C.POINTER(i64)]
   L.dfb_tsp_merge_order.argtypes = [i64, vp, i64, vp, C.POINTER(i64)]
   L.dfb_two_opt.argtypes = [vp, vp, i64, vp, i64, i64, C.POINTER(i64), vp]
+  L.dfb_write_heatmap_txt.argtypes = [C.c_char_p, i64, vp]
   for name in SYMBOLS:
     fn = getattr(L, name)
     if fn.restype is C.c_int and name not in ("dfb_abi_version",):
@@ -116,6 +117,16 @@ def tsp_merge_order(n, order):
   if rc < 0:
     _raise(rc, "dfb_tsp_merge_order: invalid argument or the order does not complete a tour")
   return tour, it.value
+
+
+def write_heatmap_txt(path, matrix):
+  """dfb_write_heatmap_txt: (n, n) matrix -> the tsp_mcts text format.  float32 input is widened exactly."""
+  m = np.ascontiguousarray(matrix, dtype=np.float64)
+  if m.ndim != 2 or m.shape[0] != m.shape[1]:
+    raise ValueError("matrix must be square")
+  rc = lib().dfb_write_heatmap_txt(os.fsencode(path), m.shape[0], m.ctypes.data)
+  if rc != DFB_OK:
+    _raise(rc, f"dfb_write_heatmap_txt: cannot write {path}")
 
 
 class Context(object):

@@ -963,3 +963,32 @@ extern "C" int dfb_two_opt(dfb_ctx* ctx, const double* points, int64_t n, int64_
   *iterations_out = hs.iterations;
   return DFB_OK;
 }
+
+// Row f4: text heat map for tsp_mcts (convert_numpy_to_txt.py:57-73).  Most entries are exactly zero after the
+// sparsification, so those are copied as a literal; the rest go through printf's correctly rounded "%.6f" (what
+// Python's f"{x:.6f}" produces as well).
+extern "C" int dfb_write_heatmap_txt(const char* path, int64_t n, const double* matrix) {
+  if (!path || !matrix || n < 1) return DFB_E_INVALID;
+  FILE* f = fopen(path, "wb");
+  if (!f) return DFB_E_INVALID;
+  std::vector<char> line((size_t)n * 28 + 2);
+  bool ok = fprintf(f, "%lld\n", (long long)n) > 0;
+  for (int64_t r = 0; r < n && ok; ++r) {
+    char* w = line.data();
+    const double* row = matrix + r * n;
+    for (int64_t c = 0; c < n; ++c) {
+      if (c) *w++ = ' ';
+      double x = row[c];
+      if (x == 0.0 && !std::signbit(x)) {
+        memcpy(w, "0.000000", 8);
+        w += 8;
+      } else {
+        w += snprintf(w, 27, "%.6f", x);
+      }
+    }
+    *w++ = '\n';
+    ok = fwrite(line.data(), 1, (size_t)(w - line.data()), f) == (size_t)(w - line.data());
+  }
+  ok = (fclose(f) == 0) && ok;
+  return ok ? DFB_OK : DFB_E_INVALID;
+}

@@ -145,6 +145,11 @@ int dfb_tsp_merge_order(int64_t n, const int64_t* order, int64_t count, int64_t*
 int dfb_two_opt(dfb_ctx* ctx, const double* points, int64_t n, int64_t* tours, int64_t batch, int64_t max_iterations,
                 int64_t* iterations_out, void* stream);
 
+/* Row f4: the MCTS solver's text heat map (tsp_mcts/convert_numpy_to_txt.py:57-73; parsed by tsp_mcts/code/TSP_IO.h:461-492):
+ * "<n>\n" then n lines of n values "%.6f" separated by one blank.  matrix (n,n) float64 HOST.  HOST code, no context.
+ * Returns DFB_E_INVALID when the file cannot be written. */
+int dfb_write_heatmap_txt(const char* path, int64_t n, const double* matrix);
+
 /* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
 int64_t dfb_launch_count(const dfb_ctx* ctx);
 

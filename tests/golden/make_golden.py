@@ -372,6 +372,38 @@ def gen_tsp_decode():
   save("tsp_decode", **out)
 
 
+def gen_mcts_txt():
+  """tsp_mcts/convert_numpy_to_txt.py of the reference, run unmodified on small dense heat maps.  The script needs
+  `fire` (absent: stubbed, main() is called directly) and np.bool (removed in numpy >= 1.24: aliased here only)."""
+  import importlib.util, types
+  sys.modules.setdefault("fire", types.ModuleType("fire"))
+  if not hasattr(np, "bool"):
+    np.bool = np.bool_
+  spec = importlib.util.spec_from_file_location(
+      "ref_convert", os.path.join(os.path.dirname(ref_shims.REFERENCE_ROOT), "tsp_mcts", "convert_numpy_to_txt.py"))
+  mod = importlib.util.module_from_spec(spec)
+  spec.loader.exec_module(mod)
+  out = {}
+  import contextlib, io
+  for case, (n, prob, seed) in enumerate([(40, 0.2, 0), (64, 0.05, 1)]):
+    rng = np.random.default_rng(seed)
+    pts = syn.tsp_points(n, seed=20 + seed, instance=0).astype(np.float32)
+    d = np.linalg.norm(pts[:, None] - pts[None], axis=-1)
+    heat = (np.exp(-5.0 * d * np.sqrt(n)) * rng.random((n, n)) + 1e-6).astype(np.float32)
+    with tempfile.TemporaryDirectory() as tmp:
+      os.makedirs(os.path.join(tmp, "numpy_heatmap"))
+      np.save(os.path.join(tmp, "numpy_heatmap", "test-heatmap-0.npy"), heat)
+      np.save(os.path.join(tmp, "numpy_heatmap", "test-points-0.npy"), pts)
+      with contextlib.redirect_stdout(io.StringIO()):
+        mod.main(tmp, os.path.join(tmp, "out"), num_nodes=n, num_files=1, expected_valid_prob=prob)
+      with open(os.path.join(tmp, "out", "heatmap", f"tsp{n}", f"heatmaptsp{n}_0.txt"), "rb") as fh:
+        text = fh.read()
+    out[f"heat{case}"], out[f"points{case}"], out[f"prob{case}"] = heat, pts, np.float64(prob)
+    out[f"txt{case}"] = np.frombuffer(text, dtype=np.uint8)
+    print("case", case, "n", n, len(text), "bytes")
+  save("mcts_txt", **out)
+
+
 if __name__ == "__main__":
   ap = argparse.ArgumentParser()
   ap.add_argument("--only", default="")
@@ -386,3 +418,5 @@ if __name__ == "__main__":
     gen_mis_decode()
   if a.only in ("", "tsp_decode"):
     gen_tsp_decode()
+  if a.only in ("", "mcts_txt"):
+    gen_mcts_txt()

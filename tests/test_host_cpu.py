@@ -153,3 +153,24 @@ def test_mis_decode_matches_reference_function():
     for i in sel:
       nb = a.indices[a.indptr[i]:a.indptr[i + 1]]
       assert not np.any(sol[nb[nb != i]])
+
+
+def test_mcts_text_export_matches_reference_converter(tmp_path):
+  """tsp_mcts/convert_numpy_to_txt.py drop-in: byte-identical files to the reference script's (tests/golden/mcts_txt.npz)."""
+  from difusco_b200.tsp_mcts import convert_numpy_to_txt as conv
+  g = golden("mcts_txt")
+  for case in range(2):
+    heat, pts, prob = g[f"heat{case}"], g[f"points{case}"], float(g[f"prob{case}"])
+    n = len(pts)
+    src = tmp_path / f"in{case}" / "numpy_heatmap"
+    src.mkdir(parents=True)
+    np.save(src / "test-heatmap-0.npy", heat)
+    np.save(src / "test-points-0.npy", pts)
+    (path,) = conv.main(str(tmp_path / f"in{case}"), str(tmp_path / f"out{case}"), num_nodes=n, num_files=1,
+                        expected_valid_prob=prob)
+    assert path.endswith(f"heatmap/tsp{n}/heatmaptsp{n}_0.txt")
+    with open(path, "rb") as fh:
+      assert fh.read() == g[f"txt{case}"].tobytes()
+  with pytest.raises(ValueError):
+    from difusco_b200 import _cabi
+    _cabi.write_heatmap_txt(str(tmp_path / "missing_dir" / "x.txt"), np.zeros((2, 2)))
