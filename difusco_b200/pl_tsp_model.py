@@ -62,69 +62,69 @@ class TSPModel(COMetaModel):
       self._fused_loop(x, steps, seed)
       return x.reshape(xt.shape)
 
+  # ------------------------------------------------------------------------------------
+  # test_step = unpack -> (sample, fused denoise loop, decode) x sequential_sampling -> metrics
+  # ------------------------------------------------------------------------------------
+  def _unpack(self, batch):
+    """The two batch layouts of the reference's datasets (pl_tsp_model.py:158-171)."""
+    if self.sparse:
+      index, graph, node_counts, _, gt_tour = batch
+      coords = graph.x.reshape((-1, 2))
+      edges = graph.edge_index.reshape((2, -1))
+      n_graphs = node_counts.shape[0]
+      labels = graph.edge_attr.reshape((n_graphs, edges.shape[1] // n_graphs))
+      return index, coords, edges, labels, gt_tour, coords.cpu().numpy(), edges.cpu().numpy()
+    index, coords, labels, gt_tour = batch
+    return index, coords, None, labels, gt_tour, coords.cpu().numpy()[0], None
+
+  def _initial_noise(self, like, copies):
+    """pl_tsp_model.py:186-199: the noise tensor is drawn twice when parallel sampling is on (only the second
+    draw is used); kept so torch's generator advances exactly as in the reference."""
+    noise = torch.randn_like(like.float())
+    if copies > 1:
+      noise = noise.repeat(copies, 1) if self.sparse else noise.repeat(copies, 1, 1)
+      noise = torch.randn_like(noise)
+    if self.diffusion_type != "gaussian":
+      noise = (noise > 0).long()
+    return (noise.reshape(-1) if self.sparse else noise).float()
+
+  def _heatmap_to_numpy(self, xt):
+    if self.diffusion_type == "gaussian":
+      return xt.cpu().detach().numpy() * 0.5 + 0.5          # :219-220
+    return xt.float().cpu().detach().numpy() + 1e-6         # :221-222
+
   def test_step(self, batch, batch_idx, split="test"):
-    edge_index = None
-    np_edge_index = None
     device = batch[-1].device
-    if not self.sparse:
-      real_batch_idx, points, adj_matrix, gt_tour = batch
-      np_points = points.cpu().numpy()[0]
-    else:
-      real_batch_idx, graph_data, point_indicator, edge_indicator, gt_tour = batch
-      points = graph_data.x.reshape((-1, 2))
-      edge_index = graph_data.edge_index.reshape((2, -1))
-      num_edges = edge_index.shape[1]
-      batch_size = point_indicator.shape[0]
-      adj_matrix = graph_data.edge_attr.reshape((batch_size, num_edges // batch_size))
-      np_points = points.cpu().numpy()
-      np_edge_index = edge_index.cpu().numpy()
-    P = self.args.parallel_sampling
-    if P > 1:
-      if not self.sparse:
-        points = points.repeat(P, 1, 1)
-      else:
-        points = points.repeat(P, 1)
-        edge_index = self.duplicate_edge_index(edge_index, np_points.shape[0], device)
-    np_gt_tour = gt_tour.cpu().numpy().reshape(-1)
-    stacked_tours, heatmaps = [], []
-    ns, merge_iterations = 0, 0
-    for _ in range(self.args.sequential_sampling):
-      xt = torch.randn_like(adj_matrix.float())
-      if P > 1:
-        xt = xt.repeat(P, 1, 1) if not self.sparse else xt.repeat(P, 1)
-        xt = torch.randn_like(xt)
-      if self.diffusion_type != "gaussian":
-        xt = (xt > 0).long()
+    index, coords, edges, labels, gt_tour, np_points, np_edge_index = self._unpack(batch)
+    copies, rounds = self.args.parallel_sampling, self.args.sequential_sampling
+    if copies > 1:
+      coords = coords.repeat(copies, 1) if self.sparse else coords.repeat(copies, 1, 1)
       if self.sparse:
-        xt = xt.reshape(-1)
-      xt = self.denoise_heatmap(points, edge_index, xt.float())
-      if self.diffusion_type == "gaussian":
-        adj_mat = xt.cpu().detach().numpy() * 0.5 + 0.5
-      else:
-        adj_mat = xt.float().cpu().detach().numpy() + 1e-6
-      heatmaps.append(adj_mat)
+        edges = self.duplicate_edge_index(edges, np_points.shape[0], device)
+    two_opt_cap = getattr(self.args, "two_opt_iterations", 1000)
+    ns, merge_iterations = 0, 0
+    heatmaps, refined = [], []
+    for _ in range(rounds):
+      heat = self._heatmap_to_numpy(self.denoise_heatmap(coords, edges, self._initial_noise(labels, copies)))
+      heatmaps.append(heat)
       if getattr(self.args, "save_numpy_heatmap", False):
-        self.run_save_numpy_heatmap(adj_mat, np_points, real_batch_idx, split)
-      tours, merge_iterations = merge_tours(adj_mat, np_points, np_edge_index, sparse_graph=self.sparse,
-                                            parallel_sampling=P,
-                                            exact=getattr(self.args, "exact_merge", True))
-      solved_tours, ns = batched_two_opt_torch(np_points.astype("float64"), np.array(tours).astype("int64"),
-                                               max_iterations=getattr(self.args, "two_opt_iterations", 1000),
-                                               device=device)
-      stacked_tours.append(solved_tours)
-    solved_tours = np.concatenate(stacked_tours, axis=0)
-    tsp_solver = TSPEvaluator(np_points)
-    gt_cost = tsp_solver.evaluate(np_gt_tour)
-    all_solved_costs = [tsp_solver.evaluate(solved_tours[i]) for i in range(P * self.args.sequential_sampling)]
-    best_solved_cost = np.min(all_solved_costs)
-    metrics = {f"{split}/gt_cost": gt_cost, f"{split}/2opt_iterations": ns,
-               f"{split}/merge_iterations": merge_iterations}
-    for k, v in metrics.items():
-      self.log(k, v, on_epoch=True, sync_dist=True)
-    self.log(f"{split}/solved_cost", best_solved_cost, prog_bar=True, on_epoch=True, sync_dist=True)
-    # not part of the reference's return value: kept for callers that want the artefacts of the last call
-    self.last_heatmap = heatmaps[-1] if len(heatmaps) == 1 else np.stack(heatmaps)
-    self.last_solved_tours, self.last_solved_cost = solved_tours, best_solved_cost
+        self.run_save_numpy_heatmap(heat, np_points, index, split)
+      tours, merge_iterations = merge_tours(heat, np_points, np_edge_index, sparse_graph=self.sparse,
+                                            parallel_sampling=copies, exact=getattr(self.args, "exact_merge", True))
+      better, ns = batched_two_opt_torch(np_points.astype("float64"), np.array(tours).astype("int64"),
+                                         max_iterations=two_opt_cap, device=device)
+      refined.append(better)
+    refined = np.concatenate(refined, axis=0)
+    scorer = TSPEvaluator(np_points)
+    best = np.min([scorer.evaluate(refined[i]) for i in range(copies * rounds)])
+    metrics = {f"{split}/gt_cost": scorer.evaluate(gt_tour.cpu().numpy().reshape(-1)),
+               f"{split}/2opt_iterations": ns, f"{split}/merge_iterations": merge_iterations}
+    for name, value in metrics.items():
+      self.log(name, value, on_epoch=True, sync_dist=True)
+    self.log(f"{split}/solved_cost", best, prog_bar=True, on_epoch=True, sync_dist=True)
+    # not part of the reference's return value: artefacts of the last call for callers that want them
+    self.last_heatmap = heatmaps[0] if rounds == 1 else np.stack(heatmaps)
+    self.last_solved_tours, self.last_solved_cost = refined, best
     return metrics
 
   def run_save_numpy_heatmap(self, adj_mat, np_points, real_batch_idx, split):
@@ -133,15 +133,13 @@ class TSPModel(COMetaModel):
     if self.args.parallel_sampling > 1 or self.args.sequential_sampling > 1:
       raise NotImplementedError("Save numpy heatmap only support single sampling")
     logger = getattr(self, "logger", None)
-    if logger is not None:
-      exp_save_dir = os.path.join(logger.save_dir, logger.name, logger.version)
-    else:
-      exp_save_dir = getattr(self.args, "storage_path", ".")
-    heatmap_path = os.path.join(exp_save_dir, "numpy_heatmap")
-    os.makedirs(heatmap_path, exist_ok=True)
-    real_batch_idx = real_batch_idx.cpu().numpy().reshape(-1)[0]
-    np.save(os.path.join(heatmap_path, f"{split}-heatmap-{real_batch_idx}.npy"), adj_mat)
-    np.save(os.path.join(heatmap_path, f"{split}-points-{real_batch_idx}.npy"), np_points)
+    root = (os.path.join(logger.save_dir, logger.name, logger.version) if logger is not None
+            else getattr(self.args, "storage_path", "."))
+    target = os.path.join(root, "numpy_heatmap")
+    os.makedirs(target, exist_ok=True)
+    tag = real_batch_idx.cpu().numpy().reshape(-1)[0]
+    np.save(os.path.join(target, f"{split}-heatmap-{tag}.npy"), adj_mat)
+    np.save(os.path.join(target, f"{split}-points-{tag}.npy"), np_points)
 
   def validation_step(self, batch, batch_idx):
     return self.test_step(batch, batch_idx, split="val")

@@ -25,12 +25,14 @@ def t_forward(tag):
   torch.cuda.synchronize()
   ctx.profile_begin()
   e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  reps = int(os.environ.get("PROBE_REPS", "1"))
   e0.record()
-  ctx.encoder_forward(xt.data_ptr(), 500.0, out.data_ptr(), st)
+  for _ in range(reps):
+    ctx.encoder_forward(xt.data_ptr(), 500.0, out.data_ptr(), st)
   e1.record()
   torch.cuda.synchronize()
   ms, n = ctx.profile_end()
-  print(f"{tag}: forward {e0.elapsed_time(e1):.2f} ms; edge kernel {ms / max(n, 1):.3f} ms/launch x{n}", flush=True)
+  print(f"{tag}: forward {e0.elapsed_time(e1) / reps:.2f} ms; edge kernel {ms / max(n, 1):.3f} ms/launch x{n}", flush=True)
   if int(os.environ.get("DFB_TC_PROBE", "0")) & 128:
     pc = ctx.debug_phase_cycles()
     ntile_cta = (E + 127) // 128 * 12 * 2      # tiles x 12 layers x (warm-up + timed forward)
