@@ -1,5 +1,5 @@
-timeout 400 python scripts/bench_decode.py --sizes 2000,5000,10000 --two_opt_iterations 300 --out gpurun_out/decode_bench_large.jsonl 2>&1 | tail -4
-timeout 200 ncu --set full --clock-control none -k regex:k_twoopt_eval -s 20 -c 1 -o gpurun_out/twoopt_eval python scripts/bench_decode.py --sizes 5000 --two_opt_iterations 40 --out /tmp/x.jsonl > gpurun_out/ncu_twoopt.log 2>&1
+timeout 400 python tests/tools/bench_decode.py --sizes 2000,5000,10000 --two_opt_iterations 300 --out gpurun_out/decode_bench_large.jsonl 2>&1 | tail -4
+timeout 200 ncu --set full --clock-control none -k regex:k_twoopt_eval -s 20 -c 1 -o gpurun_out/twoopt_eval python tests/tools/bench_decode.py --sizes 5000 --two_opt_iterations 40 --out /tmp/x.jsonl > gpurun_out/ncu_twoopt.log 2>&1
 ncu -i gpurun_out/twoopt_eval.ncu-rep --page raw --csv 2>/dev/null | python -c "
 import csv,sys
 rows=list(csv.reader(sys.stdin)); h=rows[0]; r=rows[-1]

@@ -1,8 +1,9 @@
 """Rows f2/f3 timing on the GPU box: tour merge (host C++) and batched 2-opt (CUDA) against the formulation the
 reference uses (dense N*N argsort merge on the CPU; torch (B,N,N)-temporaries 2-opt on the same GPU).
 
-    python scripts/bench_decode.py [--sizes 500,1000,2000] [--out gpurun_out/decode_bench.jsonl]
-The comparison arms are restatements from oracle/tsp_decode_oracle.py (test infrastructure), torch-on-GPU for 2-opt.
+    python tests/tools/bench_decode.py [--sizes 500,1000,2000] [--out gpurun_out/decode_bench.jsonl]
+Lives under tests/ because the comparison arms come from oracle/tsp_decode_oracle.py (test infrastructure; only tests/,
+smoke() and bench.py's CPU baseline may touch oracle/); the 2-opt arm is the same formulation with torch on the GPU.
 """
 import argparse
 import json
@@ -13,7 +14,7 @@ import time
 import numpy as np
 import torch
 
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 from difusco_b200 import synthetic as syn            # noqa: E402
 from difusco_b200.utils import tsp_utils as tu       # noqa: E402
 from oracle import tsp_decode_oracle as orc          # noqa: E402

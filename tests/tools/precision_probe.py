@@ -1,7 +1,7 @@
 """CPU probe: end-to-end error of candidate split-precision schemes for the E-row GEMMs (C, O) and the node
 linears, against the exact fp32 oracle.  Emulates operand rounding only (fp32 accumulate)."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch, torch.nn.functional as F
 from difusco_b200 import synthetic as syn
 from oracle import difusco_oracle as orc
