@@ -32,6 +32,7 @@ def t_forward(tag):
   e1.record()
   torch.cuda.synchronize()
   ms, n = ctx.profile_end()
+  print(f"{tag}: checksum {out.double().sum().item():.10e} {out.double().abs().sum().item():.10e}")
   print(f"{tag}: forward {e0.elapsed_time(e1) / reps:.2f} ms; edge kernel {ms / max(n, 1):.3f} ms/launch x{n}", flush=True)
   if int(os.environ.get("DFB_TC_PROBE", "0")) & 128:
     pc = ctx.debug_phase_cycles()
