@@ -72,8 +72,8 @@ struct TcParams {
   int w_row_base;         // row of this layer's C_hi block in the bf16 weight arena tensor map
   int n_tiles;
   unsigned long long* phase_cycles;   // [16] probe bit 7: per-phase cycle sums of worker thread 0, all CTAs
-  int probe;   // timing experiments only (DFB_TC_PROBE env): bit0 no gathers, bit1 no segment reduce, bit2 no E2,
-               // bit3 no E3 math, bit4 no E4 load/store, bit5 no conversion loads, bit6 no sigmoid
+  int probe;   // timing experiments only (DFB_TC_PROBE env): bit 0 = E1 without its gather data (--prof tuning build only),
+               // bit 7 = per-phase cycle counters (--prof build), bit 8 = no L2 prefetch of the next tile
 };
 
 // ----------------------------------------------------------------------------------------------
@@ -665,8 +665,11 @@ __device__ __forceinline__ void edge_layer_tc_body(const CUtensorMap& wmap, cons
           for (int jj = 0; jj < PC / 4; ++jj) {
             const int j = ps * (PC / 4) + jj;
             float4 a, vv;
-            if (P.probe & 1) { a = vv = make_float4(0.1f, 0.2f, 0.3f, 0.4f); }
-            else {
+#ifdef DFB_PHASE_PROF
+            if (P.probe & 1) { a = vv = make_float4(0.1f, 0.2f, 0.3f, 0.4f); }   // tuning build: time E1 without its gather data
+            else
+#endif
+            {
               a = *reinterpret_cast<const float4*>(buf + sw128_off(lane, j));
               vv = *reinterpret_cast<const float4*>(buf + sw128_off(lane, 4 + j));
             }
