@@ -6,6 +6,9 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 from difusco_b200 import synthetic as syn
+from difusco_b200 import _cabi
+if os.environ.get("DFB_LIB"):          # A/B of tuning builds: point the binding at another build of the library
+  _cabi.LIB_PATH = os.environ["DFB_LIB"]
 import gpu_util as G
 
 B = int(os.environ.get("PROBE_B", "16"))
