@@ -42,14 +42,26 @@ def batched_two_opt_torch(points, tour, max_iterations=1000, device="cuda"):
 
 def _dense_order(points, heat, edge_index):
   """The reference's visiting order (cython_merge.pyx:21, :35-38 on the matrix of tsp_utils.py:104-110): needed only
-  to resolve its ties, so it is evaluated with the same numpy expressions on the same values."""
+  to resolve its ties, so the SAME float64 keys go through the same np.argsort.  The keys are bit-identical to the
+  reference's but cost a fraction: coo(h,(c,r)).toarray() is the transpose of coo(h,(r,c)).toarray(), and
+  np.linalg.norm(p[:, None] - p, axis=-1) is sqrt(dx*dx + dy*dy) evaluated through a 3-D temporary
+  (tests/test_tsp_decode.py checks both identities bit for bit)."""
   n = points.shape[0]
-  sym = (scipy.sparse.coo_matrix((heat, (edge_index[0], edge_index[1])), shape=(n, n)).toarray() +
-         scipy.sparse.coo_matrix((heat, (edge_index[1], edge_index[0])), shape=(n, n)).toarray()).astype("double")
+  half = scipy.sparse.coo_matrix((heat, (edge_index[0], edge_index[1])), shape=(n, n)).toarray()
+  keys = (half + half.T).astype("double")
   pts = points.astype("double")
+  dist = pts[:, 0][:, None] - pts[:, 0][None, :]
+  np.multiply(dist, dist, out=dist)
+  dy = pts[:, 1][:, None] - pts[:, 1][None, :]
+  np.multiply(dy, dy, out=dy)
+  np.add(dist, dy, out=dist)
+  del dy
+  np.sqrt(dist, out=dist)
   with np.errstate(divide="ignore", invalid="ignore"):
-    keys = -sym / np.linalg.norm(pts[:, None] - pts, axis=-1)
-  return np.argsort(keys.flatten())
+    np.negative(keys, out=keys)
+    np.divide(keys, dist, out=keys)
+  del dist
+  return np.argsort(keys.reshape(-1))
 
 
 def _complete_graph(n):

@@ -240,3 +240,22 @@ def test_tsp_test_step_end_to_end(sparse_factor, par, dtype, tmp_path):
     saved = np.load(os.path.join(str(tmp_path), "numpy_heatmap", "test-heatmap-1.npy"))
     assert np.array_equal(saved, heat)
     assert np.array_equal(np.load(os.path.join(str(tmp_path), "numpy_heatmap", "test-points-1.npy")), pts)
+
+
+def test_dense_order_equals_the_reference_expression():
+  """merge_tours' exact fallback argsorts keys that are built faster than the reference builds them; the visiting
+  order must equal the reference expression's (cython_merge.pyx:21,38 on tsp_utils.py:104-110) on the same machine -
+  duplicates, self loops, negative and zero heat included."""
+  import scipy.sparse
+  rng = np.random.default_rng(3)
+  for n, e in ((40, 300), (333, 9000)):
+    pts = rng.random((n, 2)).astype(np.float32)
+    ei = rng.integers(0, n, (2, e))
+    heat = rng.standard_normal(e).astype(np.float32)
+    heat[::7] = 0.0
+    sym = (scipy.sparse.coo_matrix((heat, (ei[0], ei[1])), shape=(n, n)).toarray() +
+           scipy.sparse.coo_matrix((heat, (ei[1], ei[0])), shape=(n, n)).toarray())
+    p = pts.astype("double")
+    with np.errstate(divide="ignore", invalid="ignore"):
+      want = np.argsort((-sym.astype("double") / np.linalg.norm(p[:, None] - p, axis=-1)).flatten())
+    assert np.array_equal(tu._dense_order(pts, heat, ei), want)
