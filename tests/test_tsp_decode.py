@@ -259,3 +259,32 @@ def test_dense_order_equals_the_reference_expression():
     with np.errstate(divide="ignore", invalid="ignore"):
       want = np.argsort((-sym.astype("double") / np.linalg.norm(p[:, None] - p, axis=-1)).flatten())
     assert np.array_equal(tu._dense_order(pts, heat, ei), want)
+
+
+def test_merge_tours_equals_oracle_on_random_graphs():
+  """60 random instances (sparse with duplicate / self edges, negative and zero heat, coincident points; dense with
+  parallel sampling): the C++ merge with its exact fallback and the numpy oracle (the reference's expression on this
+  machine) give the same tours and the same merge_iterations."""
+  rng = np.random.default_rng(11)
+  for case in range(60):
+    n = int(rng.integers(3, 60))
+    pts = rng.random((n, 2)).astype(np.float32)
+    if case % 7 == 0 and n > 4:
+      pts[1] = pts[0]                                   # coincident points: +-inf keys
+    if case % 3 == 0:                                   # dense input, two samples
+      heat = rng.random((2, n, n)).astype(np.float32)
+      tours, it = tu.merge_tours(heat, pts, None, sparse_graph=False, parallel_sampling=2)
+      want = [orc.greedy_merge(pts, orc.symmetric_heat(n, h)) for h in heat]
+    else:
+      e = int(rng.integers(n, 6 * n))
+      ei = rng.integers(0, n, (2, e))
+      heat = rng.standard_normal(e).astype(np.float32) if case % 2 else rng.random(e).astype(np.float32)
+      heat[:: int(rng.integers(2, 9))] = 0.0
+      tours, it = tu.merge_tours(heat, pts, ei, sparse_graph=True)
+      want = [orc.greedy_merge(pts, orc.symmetric_heat(n, heat, ei))]
+    assert [list(map(int, w[0])) for w in want] == tours, case
+    assert it == np.mean([w[1] for w in want]), case
+    assert all(is_tour(t, n) for t in tours)
+    fast, _ = (tu.merge_tours(heat, pts, None, sparse_graph=False, parallel_sampling=2, exact=False) if case % 3 == 0
+               else tu.merge_tours(heat, pts, ei, sparse_graph=True, exact=False))
+    assert all(is_tour(t, n) for t in fast), case      # the nearest-end completion always yields a Hamiltonian cycle
