@@ -174,3 +174,26 @@ def test_mcts_text_export_matches_reference_converter(tmp_path):
   with pytest.raises(ValueError):
     from difusco_b200 import _cabi
     _cabi.write_heatmap_txt(str(tmp_path / "missing_dir" / "x.txt"), np.zeros((2, 2)))
+
+
+def test_mis_decode_yields_maximal_independent_sets():
+  """Properties of the greedy decode on random graphs (isolated nodes, ties): independent, maximal, and the first
+  node in score order is always selected."""
+  import scipy.sparse
+  from difusco_b200.utils.mis_utils import mis_decode_np
+  rng = np.random.default_rng(4)
+  for case in range(25):
+    n = int(rng.integers(2, 80))
+    m = int(rng.integers(0, 4 * n))
+    r, c = rng.integers(0, n, m), rng.integers(0, n, m)
+    keep = r != c
+    r, c = np.concatenate([r[keep], c[keep]]), np.concatenate([c[keep], r[keep]])     # undirected, as the datasets store it
+    adj = scipy.sparse.coo_matrix((np.ones(len(r)), (r, c)), shape=(n, n)).tocsr()
+    score = rng.random(n) if case % 2 else np.round(rng.random(n) * 3) / 3
+    sol = mis_decode_np(score, adj)
+    chosen = np.flatnonzero(sol)
+    assert sol.shape == (n,) and set(np.unique(sol)) <= {0, 1}
+    assert sol[np.argsort(-score)[0]] == 1
+    assert adj[chosen][:, chosen].nnz == 0                                             # independent
+    covered = np.asarray(adj[:, chosen].sum(axis=1)).reshape(-1) > 0
+    assert np.all(covered | (sol == 1))                                                # maximal
