@@ -26,6 +26,16 @@ except Exception:   # pragma: no cover - Lightning is not in this image
     def log(self, *a, **k):
       pass
 
+    @classmethod
+    def load_from_checkpoint(cls, checkpoint_path, map_location=None, strict=True, **kwargs):
+      """LightningModule.load_from_checkpoint for the call train.py:127 makes
+      (`model_class.load_from_checkpoint(ckpt_path, param_args=args)`): a Lightning .ckpt is a torch pickle whose
+      'state_dict' holds this module's keys ('model.' + GNNEncoder.state_dict())."""
+      ckpt = torch.load(checkpoint_path, map_location=map_location or "cpu", weights_only=False)
+      module = cls(**kwargs)
+      module.load_state_dict(ckpt["state_dict"] if "state_dict" in ckpt else ckpt, strict=strict)
+      return module
+
 
 def _arg(args, name, default):
   return getattr(args, name, default)

@@ -197,3 +197,24 @@ def test_mis_decode_yields_maximal_independent_sets():
     assert adj[chosen][:, chosen].nnz == 0                                             # independent
     covered = np.asarray(adj[:, chosen].sum(axis=1)).reshape(-1) > 0
     assert np.all(covered | (sol == 1))                                                # maximal
+
+
+def test_load_from_checkpoint_reads_lightning_checkpoints(tmp_path):
+  """train.py:127 `model_class.load_from_checkpoint(ckpt_path, param_args=args)`: a Lightning checkpoint written for
+  the reference module (keys 'model.<GNNEncoder key>') loads into the drop-in unchanged."""
+  from types import SimpleNamespace as NS
+  from difusco_b200 import synthetic as syn
+  from difusco_b200.pl_tsp_model import TSPModel
+  args = NS(diffusion_type="categorical", diffusion_schedule="linear", diffusion_steps=1000, sparse_factor=50, n_layers=12,
+            hidden_dim=256, aggregation="sum", parallel_sampling=1, sequential_sampling=1, inference_schedule="cosine",
+            inference_diffusion_steps=50, inference_trick="ddim")
+  w = syn.make_encoder_weights(seed=0, out_channels=2)
+  ckpt = {"state_dict": {"model." + k: torch.from_numpy(v.copy()) for k, v in w.items()}, "epoch": 3,
+          "hyper_parameters": {"param_args": None}}
+  path = tmp_path / "last.ckpt"
+  torch.save(ckpt, path)
+  m = TSPModel.load_from_checkpoint(str(path), param_args=args)
+  got = m.state_dict()
+  assert set(got) == set(ckpt["state_dict"])
+  for k, v in ckpt["state_dict"].items():
+    assert torch.equal(got[k], v), k
