@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(HERE, "libdifusco_b200.so")
 
 DFB_OK, DFB_E_INVALID, DFB_E_CUDA, DFB_E_UNSUPPORTED, DFB_E_NOMEM = 0, -1, -2, -3, -4
 CATEGORICAL, GAUSSIAN = 0, 1
-EDGE_IMPL_TC, EDGE_IMPL_FP32 = 0, 1
+EDGE_IMPL_TC, EDGE_IMPL_FP32, EDGE_IMPL_TC1 = 0, 1, 2
 AGGREGATION = {"sum": 0, "mean": 1, "max": 2}
 
 # every symbol include/difusco_b200.h declares (tests check the library exports all of them)
@@ -127,6 +127,20 @@ def write_heatmap_txt(path, matrix):
   rc = lib().dfb_write_heatmap_txt(os.fsencode(path), m.shape[0], m.ctypes.data)
   if rc != DFB_OK:
     _raise(rc, f"dfb_write_heatmap_txt: cannot write {path}")
+
+
+_DEVICE_CTX = {}
+
+
+def device_context(device_index, prefer=None):
+  """The ONE dfb_ctx per device that the helpers around the path (k-NN graph, 2-opt) run on.  A model registers its
+  own context with `prefer=` when it is created first, so model + k-NN + 2-opt share one context (and one set of
+  kernel attributes / scratch buffers) per GPU; without a model a plain context is created on first use."""
+  ctx = _DEVICE_CTX.get(device_index)
+  if ctx is None or getattr(ctx, "_h", None) is None:
+    ctx = prefer if prefer is not None else Context(device_index)
+    _DEVICE_CTX[device_index] = ctx
+  return ctx
 
 
 class Context(object):

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdifusco_b200.so")
 SOURCES = ["dfb_api.cu"]
-DEPS = ["dfb_api.cu", "common.cuh", "kernels_small.cuh", "edge_layer_fp32.cuh", "edge_layer_tc.cuh", "knn.cuh", "tsp_decode.cuh",
+DEPS = ["dfb_api.cu", "common.cuh", "kernels_small.cuh", "edge_layer_fp32.cuh", "edge_layer_tc.cuh", "edge_layer_v2.cuh", "knn.cuh", "tsp_decode.cuh",
         os.path.join("..", "..", "include", "difusco_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off"]

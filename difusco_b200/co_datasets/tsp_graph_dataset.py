@@ -22,13 +22,8 @@ except Exception:   # torch_geometric is not in this image: minimal attribute co
       self.__dict__.update(kw)
 
 
-_CTX = {}
-
-
 def _engine(device_index):
-  if device_index not in _CTX:
-    _CTX[device_index] = _cabi.Context(device_index)
-  return _CTX[device_index]
+  return _cabi.device_context(device_index)   # shared with the model and 2-opt: one dfb_ctx per GPU
 
 
 def knn_edge_index_gpu(points64, k, device=None, node_offset=0):
@@ -75,10 +70,15 @@ class TSPGraphDataset(torch.utils.data.Dataset):
       adj[tour[:-1], tour[1:]] = 1
       return index, torch.from_numpy(points).float(), torch.from_numpy(adj).float(), torch.from_numpy(tour).long()
     k = self.sparse_factor
-    edge_index = knn_edge_index_gpu(points, k, self.device)
+    if torch.utils.data.get_worker_info() is not None:
+      raise RuntimeError("difusco_b200.TSPGraphDataset builds the k-NN graph on the GPU: use num_workers=0 "
+                         "(CUDA cannot be initialised in forked DataLoader workers)")
+    # the GPU k-NN is an internal accelerator: the item is made of CPU tensors like the reference's (pin_memory and the
+    # model's own .to(device) work unchanged)
+    edge_index = knn_edge_index_gpu(points, k, self.device).cpu()
     succ = np.zeros(n, dtype=np.int64)          # tour successor of every node (:65-66)
     succ[tour[:-1]] = tour[1:]
-    succ = torch.from_numpy(succ).to(edge_index.device)
+    succ = torch.from_numpy(succ)
     tour_edges = torch.eq(edge_index[1], succ.repeat_interleave(k)).reshape(-1, 1)
     graph = GraphData(x=torch.from_numpy(points).float(), edge_index=edge_index, edge_attr=tour_edges)
     return (index, graph, torch.from_numpy(np.array([n], dtype=np.int64)).long(),

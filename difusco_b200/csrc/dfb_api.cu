@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -13,6 +14,7 @@
 #include "common.cuh"
 #include "edge_layer_fp32.cuh"
 #include "edge_layer_tc.cuh"
+#include "edge_layer_v2.cuh"
 #include "kernels_small.cuh"
 #include "knn.cuh"
 #include "tsp_decode.cuh"
@@ -48,7 +50,7 @@ struct dfb_ctx {
   DevBuf d_row, d_col, d_perm, d_rowptr, d_grp_first, d_grp_pair, d_ei_stage;
   // ---- workspace ----
   DevBuf e, h, h0, uvab, uvab0, partials, feat, tvec, tvals, gn_part, gn_stats, d_points, d_xt, d_u;
-  DevBuf opt_points, opt_tours, opt_pos, opt_dnext, opt_cand, opt_tiles, opt_state;   // 2-opt (row f3)
+  DevBuf opt_points, opt_tours, opt_pos, opt_dnext, opt_cand, opt_tiles, opt_state, opt_best;   // 2-opt (row f3)
   int tvec_steps_cap = 0;
   // ---- accounting ----
   int64_t launches = 0;
@@ -56,6 +58,8 @@ struct dfb_ctx {
   std::vector<cudaEvent_t> ev_pool;
   size_t ev_used = 0;
   TcState tc;
+  v2::State pair;   // round-2 CTA-pair kernel (middle layers of the product path)
+  bool pair_enabled = false;   // bring-up switch (DFB_PAIR_KERNEL=1) until the pair kernel is parity-green on the GPU
 };
 
 #define FAIL(ctx, code, ...)                         \
@@ -163,6 +167,16 @@ extern "C" int dfb_create(dfb_ctx** out, int device) {
     delete ctx;
     return DFB_E_CUDA;
   }
+  {
+    const char* pk = getenv("DFB_PAIR_KERNEL");
+    ctx->pair_enabled = pk && atoi(pk) != 0;
+  }
+  r = v2::init(&ctx->pair, &ctx->tc);
+  if (r != 0) {
+    g_create_error = "tcgen05 pair kernel setup failed: " + ctx->tc.err;
+    delete ctx;
+    return DFB_E_CUDA;
+  }
   *out = ctx;
   return DFB_OK;
 }
@@ -173,7 +187,8 @@ extern "C" int dfb_destroy(dfb_ctx* ctx) {
   DevBuf* bufs[] = {&ctx->wbuf, &ctx->wbuf16, &ctx->layers_dev, &ctx->d_row, &ctx->d_col, &ctx->d_perm,
                     &ctx->d_rowptr, &ctx->d_grp_first, &ctx->d_grp_pair, &ctx->d_ei_stage, &ctx->e, &ctx->h,
                     &ctx->h0, &ctx->uvab, &ctx->uvab0, &ctx->partials, &ctx->feat, &ctx->tvec, &ctx->tvals,
-                    &ctx->gn_part, &ctx->gn_stats, &ctx->d_points, &ctx->d_xt, &ctx->d_u};
+                    &ctx->gn_part, &ctx->gn_stats, &ctx->d_points, &ctx->d_xt, &ctx->d_u, &ctx->opt_points, &ctx->opt_tours,
+                    &ctx->opt_pos, &ctx->opt_dnext, &ctx->opt_cand, &ctx->opt_tiles, &ctx->opt_state, &ctx->opt_best};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   for (cudaEvent_t ev : ctx->ev_pool) cudaEventDestroy(ev);
@@ -184,7 +199,7 @@ extern "C" int dfb_destroy(dfb_ctx* ctx) {
 
 extern "C" int dfb_set_edge_impl(dfb_ctx* ctx, int impl) {
   if (!ctx) return DFB_E_INVALID;
-  if (impl != DFB_EDGE_IMPL_TC && impl != DFB_EDGE_IMPL_FP32) FAIL(ctx, DFB_E_INVALID, "unknown edge impl %d", impl);
+  if (impl != DFB_EDGE_IMPL_TC && impl != DFB_EDGE_IMPL_FP32 && impl != DFB_EDGE_IMPL_TC1) FAIL(ctx, DFB_E_INVALID, "unknown edge impl %d", impl);
   ctx->edge_impl = impl;
   return DFB_OK;
 }
@@ -384,6 +399,8 @@ extern "C" int dfb_load_weights(dfb_ctx* ctx, int n_layers, int hidden_dim, int 
   ctx->L = L; ctx->out_channels = out_channels; ctx->node_only = node_feature_only;
 
   int r = tc_bind_weights(&ctx->tc, ctx->layers.data(), L);
+  if (r) FAIL(ctx, DFB_E_CUDA, "tensor-map setup failed: %s", ctx->tc.err.c_str());
+  r = v2::bind_weights(&ctx->pair, &ctx->tc, ctx->wbuf16.p, L);
   if (r) FAIL(ctx, DFB_E_CUDA, "tensor-map setup failed: %s", ctx->tc.err.c_str());
 
   // categorical edge-embedding LUT: edge_embed(edge_pos_embed(x)) for x in {0, 1}
@@ -612,6 +629,12 @@ static int launch_edge_layer(dfb_ctx* ctx, int l, const float* uvab, const float
                                                             ctx->g, ctx->layers[l], tvec_edge, write_e,
                                                             ctx->agg_mode);
     CKL(ctx);
+  } else if (ctx->edge_impl == DFB_EDGE_IMPL_TC && ctx->pair_enabled && write_e && !e_zero && !xt_for_lut) {
+    // a middle layer (reads and writes the edge stream): the CTA-pair kernel
+    int r = v2::launch(&ctx->pair, &ctx->tc, l, (float*)ctx->e.p, uvab, (float*)ctx->partials.p, ctx->g, ctx->layers[l],
+                       tvec_edge, ctx->agg_mode, st);
+    if (r) FAIL(ctx, DFB_E_CUDA, "tcgen05 pair edge layer: %s", ctx->tc.err.c_str());
+    ctx->launches += ctx->tc.last_launches;
   } else {
     int r = tc_launch_edge_layer(&ctx->tc, l, (float*)ctx->e.p, uvab, (float*)ctx->partials.p, ctx->g,
                                  ctx->layers[l], tvec_edge, write_e, e_zero, xt_for_lut, ctx->lut,
@@ -838,9 +861,14 @@ extern "C" int dfb_debug_edge_gemm(dfb_ctx* ctx, int layer, const float* e_in, f
   if (!ctx->graph_ready) FAIL(ctx, DFB_E_INVALID, "dfb_prepare_graph must be called first");
   if (layer < 0 || layer >= ctx->L) FAIL(ctx, DFB_E_INVALID, "layer out of range");
   ctx->tc.debug_acc = acc_out;
-  int r = tc_launch_edge_layer(&ctx->tc, layer, const_cast<float*>(e_in), (const float*)ctx->uvab.p,
-                               (float*)ctx->partials.p, ctx->g, ctx->layers[layer], nullptr, 0, 0, nullptr,
-                               ctx->lut, AGG_SUM, st);
+  int r;
+  if (ctx->edge_impl == DFB_EDGE_IMPL_TC && ctx->pair_enabled)
+    r = v2::launch(&ctx->pair, &ctx->tc, layer, const_cast<float*>(e_in), (const float*)ctx->uvab.p,
+                   (float*)ctx->partials.p, ctx->g, ctx->layers[layer], nullptr, AGG_SUM, st);
+  else
+    r = tc_launch_edge_layer(&ctx->tc, layer, const_cast<float*>(e_in), (const float*)ctx->uvab.p,
+                             (float*)ctx->partials.p, ctx->g, ctx->layers[layer], nullptr, 0, 0, nullptr,
+                             ctx->lut, AGG_SUM, st);
   ctx->tc.debug_acc = nullptr;
   if (r) FAIL(ctx, DFB_E_CUDA, "tcgen05 edge layer: %s", ctx->tc.err.c_str());
   ctx->launches += 1;
@@ -915,7 +943,7 @@ extern "C" int dfb_two_opt(dfb_ctx* ctx, const double* points, int64_t n, int64_
   cudaStream_t st = (cudaStream_t)stream_;
   CK(ctx, cudaSetDevice(ctx->device));
   if (!points || !tours || !iterations_out) FAIL(ctx, DFB_E_INVALID, "two_opt: null argument");
-  if (n < 3 || n > 46340 || batch < 1 || batch > 64) FAIL(ctx, DFB_E_INVALID, "two_opt: bad size n=%lld batch=%lld (n in [3, 46340], batch in [1, 64])", (long long)n, (long long)batch);
+  if (n < 3 || n > 46340 || batch < 1 || batch > 65535) FAIL(ctx, DFB_E_INVALID, "two_opt: bad size n=%lld batch=%lld (n in [3, 46340], batch in [1, 65535])", (long long)n, (long long)batch);
   const int N = (int)n, B = (int)batch;
   for (int64_t k = 0; k < batch * (n + 1); ++k)
     if (tours[k] < 0 || tours[k] >= n) FAIL(ctx, DFB_E_INVALID, "two_opt: tour entry %lld out of range", (long long)tours[k]);
@@ -931,6 +959,7 @@ extern "C" int dfb_two_opt(dfb_ctx* ctx, const double* points, int64_t n, int64_
   ENS(ctx, ctx->opt_cand, (size_t)B * ntiles * sizeof(TwoOptCand));
   ENS(ctx, ctx->opt_tiles, (size_t)ntiles * sizeof(int2));
   ENS(ctx, ctx->opt_state, sizeof(TwoOptState));
+  ENS(ctx, ctx->opt_best, (size_t)B * sizeof(TwoOptCand));
   double* d_points = (double*)ctx->opt_points.p;
   long long* d_tours = (long long*)ctx->opt_tours.p;
   double* d_pos = (double*)ctx->opt_pos.p;
@@ -950,7 +979,8 @@ extern "C" int dfb_two_opt(dfb_ctx* ctx, const double* points, int64_t n, int64_
     for (int c = 0; c < chunk; ++c) {
       k_twoopt_eval<<<dim3(ntiles, B), 256, 0, st>>>(d_pos, d_dnext, d_tiles, d_cand, d_state, N, ntiles);
       CKL(ctx);
-      k_twoopt_apply<<<1, 1024, 0, st>>>(d_tours, d_pos, d_dnext, d_cand, d_state, N, B, ntiles, (long long)max_iterations);
+      k_twoopt_apply<<<1, 1024, 0, st>>>(d_tours, d_pos, d_dnext, d_cand, d_state, (TwoOptCand*)ctx->opt_best.p, N, B, ntiles,
+                                         (long long)max_iterations);
       CKL(ctx);
     }
     CK(ctx, cudaMemcpyAsync(&hs, d_state, sizeof(hs), cudaMemcpyDeviceToHost, st));
@@ -983,7 +1013,12 @@ extern "C" int dfb_write_heatmap_txt(const char* path, int64_t n, const double* 
         memcpy(w, "0.000000", 8);
         w += 8;
       } else {
-        w += snprintf(w, 27, "%.6f", x);
+        const int k = snprintf(w, 27, "%.6f", x);   // snprintf returns the UNtruncated length
+        if (k < 0 || k > 26) {                      // |x| >= ~1e19 or non-finite garbage: not a heat map
+          fclose(f);
+          return DFB_E_INVALID;
+        }
+        w += k;
       }
     }
     *w++ = '\n';

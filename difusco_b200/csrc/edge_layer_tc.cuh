@@ -971,6 +971,12 @@ __global__ void __launch_bounds__(TcCfg<4>::THREADS, 1)
 k_edge_layer_tc16w(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap emap, const TcParams P) {
   edge_layer_tc_body<4>(wmap, emap, P);
 }
+// the same body in linear mode (node-side / embedding linears) under its own name, so launch lists and profiles
+// do not mix the two uses
+__global__ void __launch_bounds__(TcCfg<4>::THREADS, 1)
+k_linear_tc16w(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap emap, const TcParams P) {
+  edge_layer_tc_body<4>(wmap, emap, P);
+}
 
 // ----------------------------------------------------------------------------------------------
 // host side
@@ -994,6 +1000,7 @@ struct TcState {
   const float* lin_bias = nullptr;
   int lin_rows = 0, lin_nb = 4, lin_w_row = 0;
   int wpq = 4;                  // worker warps per TMEM lane quarter (DFB_TC_WPQ tuning knob: 1, 2 or 4)
+  int probe = 0;                // DFB_TC_PROBE tuning knob, read once at context creation
   unsigned long long* phase_cycles = nullptr;
 };
 
@@ -1008,6 +1015,8 @@ inline int tc_init(TcState* st, int num_sms) {
     e = cudaFuncSetAttribute(k_edge_layer_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<2>::SMEM_ALLOC);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(k_edge_layer_tc16w, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<4>::SMEM_ALLOC);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(k_linear_tc16w, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<4>::SMEM_ALLOC);
   if (e != cudaSuccess) {
     st->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e);
     return -2;
@@ -1016,6 +1025,8 @@ inline int tc_init(TcState* st, int num_sms) {
     const char* w = getenv("DFB_TC_WPQ");
     st->wpq = w ? atoi(w) : 4;
     if (st->wpq != 1 && st->wpq != 2 && st->wpq != 4) st->wpq = 4;
+    const char* pe = getenv("DFB_TC_PROBE");
+    st->probe = pe ? atoi(pe) : 0;
   }
   if ((e = cudaMalloc(&st->zero_row, H * sizeof(float))) != cudaSuccess ||
       (e = cudaMemset(st->zero_row, 0, H * sizeof(float))) != cudaSuccess ||
@@ -1066,6 +1077,27 @@ inline int tc_bind_weights(TcState* st, const LayerParams* layers, int L) {
   return 0;
 }
 
+// fp32 edge stream [E_pad][256] as a 2-D tensor map: box 32 columns x 128 rows, 128-byte swizzle (re-encoded only when
+// the buffer or its size changes)
+inline int tc_ensure_emap(TcState* st, const float* e, int E) {
+  const long long e_rows = (long long)((E + TC_TILE - 1) / TC_TILE) * TC_TILE;
+  if (st->emap_ptr == (const void*)e && st->emap_rows == e_rows) return 0;
+  cuuint64_t gdim[2] = {(cuuint64_t)H, (cuuint64_t)e_rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)H * sizeof(float)};
+  cuuint32_t box[2] = {32u, (cuuint32_t)TC_TILE};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = ((PFN_encodeTiled)st->encode_fn)(&st->emap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)e, gdim, gstride,
+                                                box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    st->err = "cuTensorMapEncodeTiled(e) failed with CUresult " + std::to_string((int)r);
+    return -2;
+  }
+  st->emap_ptr = (const void*)e;
+  st->emap_rows = e_rows;
+  return 0;
+}
+
 inline int tc_launch_edge_layer(TcState* st, int l, float* e, const float* uvab, float* partials, GraphDev g,
                                 LayerParams lp, const float* tvec_edge, int write_e, int e_zero,
                                 const float* xt_lut, const float* lut, int agg_mode, cudaStream_t stream) {
@@ -1074,21 +1106,9 @@ inline int tc_launch_edge_layer(TcState* st, int l, float* e, const float* uvab,
     st->err = "weights not bound";
     return -1;
   }
-  const long long e_rows = (long long)((g.E + TC_TILE - 1) / TC_TILE) * TC_TILE;
-  if (!st->lin_out && (st->emap_ptr != (const void*)e || st->emap_rows != e_rows)) {   // linear mode never touches it
-    cuuint64_t gdim[2] = {(cuuint64_t)H, (cuuint64_t)e_rows};
-    cuuint64_t gstride[1] = {(cuuint64_t)H * sizeof(float)};
-    cuuint32_t box[2] = {32u, (cuuint32_t)TC_TILE};
-    cuuint32_t estr[2] = {1u, 1u};
-    CUresult r = ((PFN_encodeTiled)st->encode_fn)(&st->emap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)e, gdim, gstride,
-                                                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-      st->err = "cuTensorMapEncodeTiled(e) failed with CUresult " + std::to_string((int)r);
-      return -2;
-    }
-    st->emap_ptr = (const void*)e;
-    st->emap_rows = e_rows;
+  if (!st->lin_out) {   // linear mode never touches the edge stream
+    int r = tc_ensure_emap(st, e, g.E);
+    if (r) return r;
   }
   TcParams P;
   P.e = e; P.uvab = uvab; P.partials = partials; P.g = g; P.lp = lp; P.tvec = tvec_edge;
@@ -1102,12 +1122,10 @@ inline int tc_launch_edge_layer(TcState* st, int l, float* e, const float* uvab,
   P.lin_nb = st->lin_nb; P.lin_w_row = st->lin_w_row;
   P.n_tiles = st->lin_out ? st->lin_nb * ((st->lin_rows + TC_TILE - 1) / TC_TILE) : (g.E + TC_TILE - 1) / TC_TILE;
   if (st->lin_out) P.write_e = 0;
-  {
-    const char* pe = getenv("DFB_TC_PROBE");
-    P.probe = pe ? atoi(pe) : 0;
-  }
+  P.probe = st->probe;
   int grid = P.n_tiles < st->num_sms ? P.n_tiles : st->num_sms;
   if (st->wpq == 1) k_edge_layer_tc<1><<<grid, TcCfg<1>::THREADS, TcCfg<1>::SMEM_ALLOC, stream>>>(st->wmap, st->emap, P);
+  else if (st->wpq == 4 && st->lin_out) k_linear_tc16w<<<grid, TcCfg<4>::THREADS, TcCfg<4>::SMEM_ALLOC, stream>>>(st->wmap, st->emap, P);
   else if (st->wpq == 4) k_edge_layer_tc16w<<<grid, TcCfg<4>::THREADS, TcCfg<4>::SMEM_ALLOC, stream>>>(st->wmap, st->emap, P);
   else k_edge_layer_tc<2><<<grid, TcCfg<2>::THREADS, TcCfg<2>::SMEM_ALLOC, stream>>>(st->wmap, st->emap, P);
   cudaError_t err = cudaGetLastError();

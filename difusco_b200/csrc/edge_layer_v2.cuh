@@ -1,0 +1,837 @@
+// Fused GNN edge layer, round-2 kernel: CTA pairs (tcgen05 cta_group::2), software-pipelined over tiles.
+//
+//   e_hat = C e + A h[col] + B h[row]                         gnn_encoder.py:104,110
+//   agg  += sigmoid(e_hat) * V h[col]   (row-segment sums)     :112,163,177-191
+//   e_til = relu(LN_e(e_hat)) + tau                            :131,135,445
+//   e     = e + O silu(LN_O(e_til)) + b_O   (in place)         :449, :339-347
+//
+// What changed against edge_layer_tc.cuh (which stays for layer 0, the MIS last layer and the linear mode):
+//  * Two CTAs of a cluster work as ONE tensor-core unit: M = 256 (one 128-edge tile per CTA), N = 256, the weight
+//    operand B is split by output channel between the two CTAs (each CTA streams only HALF of C and O: the
+//    L2 -> SM weight traffic and the shared-memory footprint of B halve).  MMAs are issued by the leader CTA only;
+//    completion is multicast to both CTAs' mbarriers.
+//  * The fp32 edge tile comes in by TMA (32-column boxes, 128B swizzle) into the operand ring and is converted
+//    IN PLACE to the bf16 hi/lo K-major operand (64B swizzle): the round-1 kernel's register-staged global loads
+//    (30 % of all warp samples, long-scoreboard) are gone.
+//  * The operand rings (3 x 16 KB A, 3 x 16 KB B) no longer alias the gather / epilogue staging, so the phases of
+//    neighbouring tiles overlap: conversion + GEMM1 of tile t+1 run under E4 of tile t ("X phase"), the
+//    residual tile for E4 is fetched and the result stored by a dedicated I/O warp through a 3-box ring.
+//  * E1 takes all of its inputs (A h[col], V h[col], B h[row]) from warp-private cp.async staging that is
+//    filled two 8-column steps ahead; the segment-reduce patch reuses the staging buffer.
+//
+// Warp roles (640 threads): warp 0 weight TMA, warp 1 MMA issue + TMEM owner, warp 2 edge-index prefetch + input-box
+// TMA, warp 3 E4 residual loads / result stores, warps 4..19 row workers (thread == edge row == TMEM lane, the 256
+// channels of a row split over the 4 warps of a lane quarter).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "edge_layer_tc.cuh"
+
+namespace dfb {
+namespace v2 {
+
+constexpr int NA = 3, NB = 3, NOUT = 3;
+constexpr int STAGE = 16384;                       // one fp32 box [128 rows x 32 cols] == bf16 hi (8 KB) | lo (8 KB)
+constexpr int HALF = 8192;
+constexpr int NWORKW = 16;                         // worker warps
+constexpr int NSERV = 4;                           // service warps
+constexpr int THREADS = (NSERV + NWORKW) * 32;     // 640
+constexpr int NWORK = NWORKW * 32;                 // 512
+constexpr int GBUF = 2048 + 128;                   // gather buffer: [32 rows][8 A | 8 V] fp32 + 4 B-row slots x 32 B
+constexpr int OFF_A = 0;
+constexpr int OFF_B = OFF_A + NA * STAGE;
+constexpr int OFF_OUT = OFF_B + NB * STAGE;
+constexpr int OFF_G = OFF_OUT + NOUT * STAGE;
+constexpr int OFF_PRM = OFF_G + NWORKW * 2 * GBUF;  // ln_e_g, ln_e_b, tau, ln_o_g, ln_o_b, b_O
+constexpr int OFF_IDX = OFF_PRM + 6 * H * 4;        // 2 buffers x { row[128], col[128] }
+constexpr int OFF_BAR = OFF_IDX + 2 * 2 * TC_TILE * 4;
+constexpr int SMEM_BYTES = OFF_BAR + 36 * 8;
+static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+static_assert(GBUF % 128 == 0, "gather buffers stay 128-byte aligned");
+
+// UMMA instruction descriptor: D=F32, A=B=BF16, K-major, N=256, M=256 (the pair), cute::UMMA::InstrDescriptor
+constexpr uint32_t IDESC2 = (1u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((256u >> 4) << 24);
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address (cute Sm100MmaPeerBitMask)
+
+struct Params {
+  float* e;
+  const float* uvab;
+  float* partials;
+  GraphDev g;
+  LayerParams lp;
+  const float* tvec;      // [256] time vector added on edges (TSP) or nullptr (MIS)
+  float* debug_acc;       // tests: dump the GEMM1 accumulator [E][256] and stop
+  int* error_flag;
+  unsigned long long* phase_cycles;
+  int agg_mode;
+  int w_row_base;         // row of this layer's C_hi block in the bf16 weight arena
+  int n_tiles;
+  int probe;
+};
+
+// ----------------------------------------------------------------------------------------------
+// PTX wrappers specific to the pair kernel
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive (release at cluster scope) on the LEADER CTA's copy of a barrier, from either CTA of the pair
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_MASK) : "memory");
+}
+// bounded wait with cluster-scope acquire: pairs with mbar_arrive_leader from the peer CTA
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity, int* error_flag, int code) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok = 0;
+#pragma unroll 1
+  for (uint32_t spin = 0;; ++spin) {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity), "r"(20000u)
+        : "memory");
+    if (ok) return;
+    if (spin > 400000u) {
+      if (error_flag) {
+        error_flag[1] = (int)blockIdx.x;
+        error_flag[2] = (int)parity;
+        error_flag[3] = (int)threadIdx.x;
+        atomicExch(error_flag, code);
+      }
+      __threadfence_system();
+      __trap();
+    }
+  }
+}
+// TMA load whose completion is booked on the leader CTA's barrier (cute SM100_TMA_2SM_LOAD_2D)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & PEER_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
+      " tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(IDESC2), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
+      " tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(IDESC2), "r"(accumulate)
+      : "memory");
+}
+// completion of all prior MMAs of this thread -> the barrier at the same offset in BOTH CTAs
+__device__ __forceinline__ void umma2_commit(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+      : "memory");
+}
+// K-major, 64-byte swizzle, 8-row atoms 512 bytes apart (cute::UMMA::SmemDescriptor, layout type 4)
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
+  const uint64_t hi = 32ull | (1ull << 14) | (4ull << 29);
+  return (hi << 32) | (1ull << 16) | (uint64_t)((smem_addr >> 4) & 0x3fffu);
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%8], {%0, %1, %2, %3, %4, %5, %6, %7};"
+               ::"r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(taddr)
+               : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read_n() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// byte offset of (row r, 16-byte unit j in [0,4)) inside a [rows][32 bf16] K-major 64B-swizzled tile
+__device__ __forceinline__ uint32_t sw64_off(int r, int j) {
+  return (uint32_t)((r >> 3) * 512 + (r & 7) * 64 + ((j ^ ((r >> 1) & 3)) << 4));
+}
+
+// ----------------------------------------------------------------------------------------------
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap emap, const Params P) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  float* prm = reinterpret_cast<float*>(smem + OFF_PRM);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  // box_full: TMA input box landed (local).  TWO barriers per stage (even / odd use of the stage): the converting parts
+  // visit a stage only every other use (part p converts boxes p and p + 4), and a parity wait that is two phases ahead of
+  // the barrier aliases with the phase before - with one barrier per (stage, use parity) a waiter is never more than one
+  // phase ahead.
+  uint64_t* box_full = bars;        // [2 * NA]
+  uint64_t* a_full = bars + 6;      // [NA] LEADER: stage converted by both CTAs (4 warps each)
+  uint64_t* a_empty = bars + 9;     // [NA] MMA commit (multicast): stage consumed
+  uint64_t* b_full = bars + 12;     // [NB] LEADER: both weight halves landed (tx)
+  uint64_t* b_empty = bars + 15;    // [NB] MMA commit (multicast)
+  uint64_t* acc_rdy = bars + 18;    // [2]  MMA commit (multicast): GEMM1 / GEMM2 accumulator complete
+  uint64_t* a2_full = bars + 20;    // [4]  LEADER: GEMM2 A chunk (64 columns of s) written to TMEM by both CTAs
+  uint64_t* res_full = bars + 24;   // [NOUT] residual box landed (local, tx)
+  uint64_t* out_full = bars + 27;   // [NOUT] result box written by the 16 worker warps
+  uint64_t* idx_full = bars + 30;   // [2]  edge endpoints of a tile in shared memory (32 lanes of warp 2)
+  uint64_t* idx_free = bars + 32;   // [2]  the 16 worker warps are done with them
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 34);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int n_clusters = gridDim.x >> 1, cid = blockIdx.x >> 1;
+  const int n_pairs = (P.n_tiles + 1) >> 1;
+  const int n_my = (cid < n_pairs) ? (n_pairs - cid + n_clusters - 1) / n_clusters : 0;
+  const bool debug = P.debug_acc != nullptr;
+  const uint32_t smem_base = smem_u32(smem);
+  auto tile_of = [&](int it) { return 2 * (cid + it * n_clusters) + (int)rank; };
+
+  if (threadIdx.x == 0) {
+    if (smem_base & 1023u) {   // the operand swizzles assume a 1024-byte aligned base
+      if (P.error_flag) atomicExch(P.error_flag, 99);
+      __trap();
+    }
+    for (int i = 0; i < NA; ++i) { mbar_init(&box_full[2 * i], 1); mbar_init(&box_full[2 * i + 1], 1); mbar_init(&a_full[i], 8); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    mbar_init(&acc_rdy[0], 1); mbar_init(&acc_rdy[1], 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&a2_full[i], 2 * NWORKW);
+    for (int i = 0; i < NOUT; ++i) { mbar_init(&res_full[i], 1); mbar_init(&out_full[i], NWORKW); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&idx_full[i], 32); mbar_init(&idx_free[i], NWORKW); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_proxy_async();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < H; i += THREADS) {
+    prm[i] = P.lp.ln_e_g[i];
+    prm[H + i] = P.lp.ln_e_b[i];
+    prm[2 * H + i] = P.tvec ? P.tvec[i] : 0.0f;
+    prm[3 * H + i] = P.lp.ln_o_g[i];
+    prm[4 * H + i] = P.lp.ln_o_b[i];
+    prm[5 * H + i] = P.lp.b_O[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // both CTAs' barriers are initialised before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================== weight TMA (both CTAs, each its N-half) =====================================
+    if (lane == 0) {
+      const int n_use = debug ? 8 : 16;
+      uint32_t u = 0;
+      for (int it = 0; it < n_my; ++it) {
+        for (int i = 0; i < n_use; ++i, ++u) {
+          const uint32_t sb = u % NB, k = u / NB;
+          mbar_wait(&b_empty[sb], (k & 1) ^ 1, P.error_flag, 1);
+          if (leader) mbar_arrive_expect_tx(&b_full[sb], 2 * STAGE);
+          const uint32_t dst = smem_base + OFF_B + sb * STAGE;
+          // arena rows of a layer: C_hi | C_lo | O_hi | O_lo (256 each); this CTA's output channels are rows rank*128..+127
+          const int rb = P.w_row_base + (i < 8 ? 0 : 512) + (int)rank * 128, kc = (i & 7) * 32;
+          tma_load_2d_pair(dst, &wmap, &b_full[sb], kc, rb);
+          tma_load_2d_pair(dst + HALF, &wmap, &b_full[sb], kc, rb + 256);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issue (leader CTA only) =====================================
+    if (leader && lane == 0) {
+      uint32_t ub = 0, ga = 0;
+      for (int it = 0; it < n_my; ++it) {
+        // ---- GEMM1: acc1 = e C^T, 8 K-chunks of 32, A and B from shared memory ----
+        for (int kc = 0; kc < 8; ++kc, ++ub, ++ga) {
+          const uint32_t sb = ub % NB, sa = ga % NA;
+          mbar_wait(&b_full[sb], (ub / NB) & 1, P.error_flag, 2);
+          mbar_wait_cluster(&a_full[sa], (ga / NA) & 1, P.error_flag, 3);
+          tc_fence_after();
+          const uint32_t a_hi = smem_base + OFF_A + sa * STAGE, a_lo = a_hi + HALF;
+          const uint32_t b_hi = smem_base + OFF_B + sb * STAGE, b_lo = b_hi + HALF;
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            const uint64_t dah = umma_desc_sw64(a_hi + ks * 32), dal = umma_desc_sw64(a_lo + ks * 32);
+            const uint64_t dbh = umma_desc_sw64(b_hi + ks * 32), dbl = umma_desc_sw64(b_lo + ks * 32);
+            umma2_bf16(tmem_base, dah, dbh, (kc | ks) ? 1u : 0u);
+            umma2_bf16(tmem_base, dal, dbh, 1u);
+            umma2_bf16(tmem_base, dah, dbl, 1u);
+          }
+          umma2_commit(&a_empty[sa]);
+          umma2_commit(&b_empty[sb]);
+        }
+        umma2_commit(&acc_rdy[0]);
+        if (debug) continue;
+        // ---- GEMM2: acc2 = s O^T, A operand (bf16 hi/lo of s) in TMEM: k-step j at columns 16 j (8 hi + 8 lo) ----
+        for (int kc = 0; kc < 8; ++kc, ++ub) {
+          const uint32_t sb = ub % NB;
+          if ((kc & 1) == 0) mbar_wait_cluster(&a2_full[kc >> 1], it & 1, P.error_flag, 13);
+          mbar_wait(&b_full[sb], (ub / NB) & 1, P.error_flag, 12);
+          tc_fence_after();
+          const uint32_t b_hi = smem_base + OFF_B + sb * STAGE, b_lo = b_hi + HALF;
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            const uint32_t ta_hi = tmem_base + (uint32_t)(kc * 32 + ks * 16), ta_lo = ta_hi + 8;
+            const uint64_t dbh = umma_desc_sw64(b_hi + ks * 32), dbl = umma_desc_sw64(b_lo + ks * 32);
+            umma2_bf16_ts(tmem_base + 256u, ta_hi, dbh, (kc | ks) ? 1u : 0u);
+            umma2_bf16_ts(tmem_base + 256u, ta_lo, dbh, 1u);
+            umma2_bf16_ts(tmem_base + 256u, ta_hi, dbl, 1u);
+          }
+          umma2_commit(&b_empty[sb]);
+        }
+        umma2_commit(&acc_rdy[1]);
+      }
+    }
+  } else if (warp == 2) {
+    // ===================================== edge endpoints + input boxes =====================================
+    uint32_t ga = 0;
+    for (int it = 0; it < n_my; ++it) {
+      const int tile = tile_of(it), ib = it & 1;
+      if (it >= 2) mbar_wait(&idx_free[ib], ((it >> 1) - 1) & 1, P.error_flag, 20);
+      int* s_row = reinterpret_cast<int*>(smem + OFF_IDX) + ib * 2 * TC_TILE;
+      int* s_col = s_row + TC_TILE;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int rr = j * 32 + lane, s_edge = tile * TC_TILE + rr;
+        const bool ok = tile < P.n_tiles && s_edge < P.g.E;
+        s_row[rr] = ok ? __ldg(P.g.row + s_edge) : -1;
+        s_col[rr] = ok ? __ldg(P.g.col + s_edge) : 0;
+      }
+      mbar_arrive(&idx_full[ib]);
+      if (lane == 0) {
+        if (it + 1 < n_my && tile_of(it + 1) < P.n_tiles && !(P.probe & 256)) {
+          // the next tile's 128 edge rows are one contiguous 128 KB block: pull it into L2 now
+          const float* nxt = P.e + (size_t)tile_of(it + 1) * TC_TILE * H;
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nxt), "r"(TC_TILE * H * 4) : "memory");
+        }
+        for (int b = 0; b < 8; ++b, ++ga) {
+          const uint32_t sa = ga % NA;
+          mbar_wait(&a_empty[sa], ((ga / NA) & 1) ^ 1, P.error_flag, 4);
+          uint64_t* bf = &box_full[2 * sa + ((ga / NA) & 1)];
+          mbar_arrive_expect_tx(bf, STAGE);
+          tma_load_2d(smem_base + OFF_A + sa * STAGE, &emap, bf, 32 * b, tile * TC_TILE);
+        }
+      }
+      __syncwarp();
+    }
+  } else if (warp == 3) {
+    // ===================================== E4 I/O: residual boxes in, result boxes out =====================================
+    if (lane == 0 && !debug) {
+      const int total = n_my * 8;
+      for (int h = 0; h < total + 2; ++h) {
+        if (h >= 2) {
+          const int hs = h - 2, slot = hs % NOUT;
+          mbar_wait(&out_full[slot], (hs / NOUT) & 1, P.error_flag, 8);
+          tma_store_2d(&emap, smem_base + OFF_OUT + slot * STAGE, 32 * (hs & 7), tile_of(hs >> 3) * TC_TILE);
+          tma_store_commit();
+        }
+        if (h < total) {
+          if (h >= NOUT) tma_store_wait_read_n<1>();   // the store that last used this slot (box h-3) has read it
+          const int slot = h % NOUT;
+          mbar_arrive_expect_tx(&res_full[slot], STAGE);
+          tma_load_2d(smem_base + OFF_OUT + slot * STAGE, &emap, &res_full[slot], 32 * (h & 7), tile_of(h >> 3) * TC_TILE);
+        }
+      }
+      tma_store_wait_all();
+    }
+  } else {
+    // ===================================== row workers =====================================
+    const int wq = warp & 3;                 // TMEM lane quarter this warp may access (hardware rule: warp id % 4)
+    const int ww = warp - NSERV;             // 0..15 == part * 4 + wq
+    const int part = ww >> 2;                // which 64-column slice of the row
+    const int r = wq * 32 + lane;            // tile row == TMEM lane
+    const int cbase = part * 64;
+    unsigned char* gbuf0 = smem + OFF_G + ww * 2 * GBUF;
+    const uint32_t t_acc1 = tmem_base + ((uint32_t)(wq * 32) << 16);
+    const uint32_t t_acc2 = t_acc1 + 256u;
+    auto worker_bar = [] { asm volatile("bar.sync 1, %0;" ::"n"(NWORK) : "memory"); };
+    auto stat_buf = [&](int p2) { return reinterpret_cast<float*>(smem + OFF_G + (p2 * 4 + wq) * 2 * GBUF); };
+#ifdef DFB_PHASE_PROF
+    const bool prof = (P.probe & 128) && ww == 0 && lane == 0;
+    long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tp = 0;
+#define PHASE(i) do { if (prof) { long long _n = clock64(); pc[i] += _n - tp; tp = _n; } } while (0)
+#else
+#define PHASE(i) do { } while (0)
+#endif
+    uint32_t gbox = 0;   // global input-box counter of this CTA (operand ring position)
+    for (int it = 0; it <= n_my; ++it) {
+      const bool have_tile = it < n_my;      // X phase converts tile `it` and finishes (E4) tile `it - 1`
+      const int tile = tile_of(it);
+#ifdef DFB_PHASE_PROF
+      if (prof) tp = clock64();
+#endif
+      worker_bar();   // every warp has left E3 of the previous tile: the gather buffers (LayerNorm exchange) are free
+      int my_row = -1, my_col = 0;
+      uint32_t seg_mask = 0;
+      const float* gptr[4] = {nullptr, nullptr, nullptr, nullptr};
+      const float* bptr = nullptr;
+      int nseg = 0;
+      const uint32_t goff = (uint32_t)((lane >> 2) * 64 + (((lane & 3) ^ ((lane >> 3) & 3)) << 4));
+      auto gather_issue = [&](int step, unsigned char* buf) {
+        const uint32_t b32 = smem_u32(buf);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) cp_async16(b32 + j * 512 + goff, gptr[j] + step * 8);
+        if (bptr) cp_async16(b32 + 2048 + lane * 16, bptr + step * 8);
+        cp_async_commit();
+      };
+      if (have_tile) {
+        const int ib = it & 1;
+        mbar_wait(&idx_full[ib], (it >> 1) & 1, P.error_flag, 21);
+        const int* s_row = reinterpret_cast<const int*>(smem + OFF_IDX) + ib * 2 * TC_TILE;
+        const int* s_col = s_row + TC_TILE;
+        my_row = s_row[r];
+        my_col = s_col[r];
+        const bool valid = my_row >= 0;
+        {
+          int next_row = __shfl_down_sync(0xffffffffu, my_row, 1);
+          bool seg_end = valid && (lane == 31 || next_row != my_row);
+          seg_mask = __ballot_sync(0xffffffffu, seg_end);
+        }
+        nseg = __popc(seg_mask);
+        // A h[col] | V h[col]: lane moves 16-byte unit (lane & 3) of rows (j*8 + lane/4); units 0,1 = A, 2,3 = V
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int cj = s_col[wq * 32 + j * 8 + (lane >> 2)], uu = lane & 3;
+          gptr[j] = P.uvab + (size_t)cj * 4 * H + ((uu < 2) ? 2 * H : H) + cbase + (uu & 1) * 4;
+        }
+        // B h[row]: one 32-byte slot per node segment of this warp (up to 4; more -> direct loads in E1)
+        {
+          const int sl = (lane >> 1) & 3;
+          const int pos = (int)__fns(seg_mask, 0, sl + 1);
+          const int node = __shfl_sync(0xffffffffu, my_row, (pos >= 0 && pos < 32) ? pos : 0);
+          if (lane < 8 && sl < nseg && nseg <= 4) bptr = P.uvab + (size_t)node * 4 * H + 3 * H + cbase + (lane & 1) * 4;
+        }
+        if (!debug) {
+          gather_issue(0, gbuf0);
+          gather_issue(1, gbuf0 + GBUF);
+        }
+      }
+
+      // ================= X phase: convert this tile's boxes (part == box & 3), finish the previous tile (E4) =================
+      for (int b = 0; b < 8; ++b) {
+        // every part observes every phase of the box barriers in order (a parity wait must never run two phases ahead);
+        // the owner of the box (part == b & 3) converts it
+        const uint32_t g = gbox + b, sa = g % NA;
+        if (have_tile) mbar_wait(&box_full[2 * sa + ((g / NA) & 1)], (g / (2 * NA)) & 1, P.error_flag, 5);
+        if (have_tile && (b & 3) == part) {
+          unsigned char* stage = smem + OFF_A + sa * STAGE;
+          uint4 hi[4], lo[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 x0 = *reinterpret_cast<const float4*>(stage + sw128_off(r, 2 * j));
+            const float4 x1 = *reinterpret_cast<const float4*>(stage + sw128_off(r, 2 * j + 1));
+            uint2 h0, l0, h1, l1;
+            split4(x0, h0, l0);
+            split4(x1, h1, l1);
+            hi[j] = make_uint4(h0.x, h0.y, h1.x, h1.y);
+            lo[j] = make_uint4(l0.x, l0.y, l1.x, l1.y);
+          }
+          // in place: all 128 rows of the box have been read before any bf16 row is written over them
+          asm volatile("bar.sync %0, 128;" ::"r"(2 + part) : "memory");
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            *reinterpret_cast<uint4*>(stage + sw64_off(r, j)) = hi[j];
+            *reinterpret_cast<uint4*>(stage + HALF + sw64_off(r, j)) = lo[j];
+          }
+          fence_proxy_async();
+          tc_fence_before();   // orders this thread's earlier TMEM accesses (previous tile) before the MMA overwrites acc1
+          __syncwarp();
+          if (lane == 0) mbar_arrive_leader(&a_full[sa]);
+        }
+        if (it > 0 && !debug) {
+          const uint32_t hh = (uint32_t)(it - 1) * 8 + b, slot = hh % NOUT;
+          if (b == 0) {
+            mbar_wait(&acc_rdy[1], (it - 1) & 1, P.error_flag, 7);
+            tc_fence_after();
+          }
+          mbar_wait(&res_full[slot], (hh / NOUT) & 1, P.error_flag, 10);
+          uint32_t v[8];
+          tmem_ld8(t_acc2 + 32 * b + 8 * part, v);
+          unsigned char* box = smem + OFF_OUT + slot * STAGE;
+          float4* s0 = reinterpret_cast<float4*>(box + sw128_off(r, 2 * part));
+          float4* s1 = reinterpret_cast<float4*>(box + sw128_off(r, 2 * part + 1));
+          const float4 e0 = *s0, e1 = *s1;
+          const float4 bo0 = *reinterpret_cast<const float4*>(prm + 5 * H + 32 * b + 8 * part);
+          const float4 bo1 = *reinterpret_cast<const float4*>(prm + 5 * H + 32 * b + 8 * part + 4);
+          tmem_wait_ld();
+          const float2 o0 = add2(add2(make_float2(e0.x, e0.y), make_float2(__uint_as_float(v[0]), __uint_as_float(v[1]))), make_float2(bo0.x, bo0.y));
+          const float2 o1 = add2(add2(make_float2(e0.z, e0.w), make_float2(__uint_as_float(v[2]), __uint_as_float(v[3]))), make_float2(bo0.z, bo0.w));
+          const float2 o2 = add2(add2(make_float2(e1.x, e1.y), make_float2(__uint_as_float(v[4]), __uint_as_float(v[5]))), make_float2(bo1.x, bo1.y));
+          const float2 o3 = add2(add2(make_float2(e1.z, e1.w), make_float2(__uint_as_float(v[6]), __uint_as_float(v[7]))), make_float2(bo1.z, bo1.w));
+          *s0 = make_float4(o0.x, o0.y, o1.x, o1.y);
+          *s1 = make_float4(o2.x, o2.y, o3.x, o3.y);
+          fence_proxy_async();   // generic-proxy writes -> visible to the TMA store
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&out_full[slot]);
+        }
+      }
+      gbox += 8;
+      PHASE(0);   // X phase
+      if (!have_tile) break;
+
+      const bool valid = my_row >= 0;
+      const int s_edge = tile * TC_TILE + r;
+      mbar_wait(&acc_rdy[0], it & 1, P.error_flag, 6);
+      tc_fence_after();
+      PHASE(1);   // wait for GEMM1
+      if (debug) {
+#pragma unroll 1
+        for (int c0 = cbase; c0 < cbase + 64; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(t_acc1 + c0, v);
+          tmem_wait_ld();
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              __stcg(reinterpret_cast<float4*>(P.debug_acc + (size_t)s_edge * H + c0) + j,
+                     make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                 __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&idx_free[it & 1]);
+        continue;
+      }
+
+      // ================= E1: e_hat, gate, messages, row statistics (8 steps of 8 columns) =================
+      const int grp = tile * 4 + wq;
+      const int first_node = (grp < P.g.n_groups) ? __ldg(P.g.grp_first + grp) : 0;
+      const size_t pair_base = (grp < P.g.n_groups) ? (size_t)__ldg(P.g.grp_pair + grp) : 0;
+      const int slot_b = min(__popc(seg_mask & ((1u << lane) - 1u)), 3);
+      const float* b_direct = (nseg > 4) ? P.uvab + (size_t)(valid ? my_row : 0) * 4 * H + 3 * H + cbase : nullptr;
+      const uint32_t sw_a = (uint32_t)((lane >> 1) & 3);
+      float2 nK = splat2(0.f), S1p = splat2(0.f), S1q = splat2(0.f), Q1p = splat2(0.f), Q1q = splat2(0.f);
+#pragma unroll 1
+      for (int step = 0; step < 8; ++step) {
+        const int c0 = cbase + step * 8;
+        unsigned char* buf = gbuf0 + (step & 1) * GBUF;
+        uint32_t v[8];
+        tmem_ld8(t_acc1 + c0, v);
+        if (step < 7) cp_async_wait<1>(); else cp_async_wait<0>();
+        __syncwarp();                       // this warp's pieces of the step have landed
+        const unsigned char* rowp = buf + lane * 64;
+        const float4 a0 = *reinterpret_cast<const float4*>(rowp + ((0u ^ sw_a) << 4));
+        const float4 a1 = *reinterpret_cast<const float4*>(rowp + ((1u ^ sw_a) << 4));
+        const float4 v0 = *reinterpret_cast<const float4*>(rowp + ((2u ^ sw_a) << 4));
+        const float4 v1 = *reinterpret_cast<const float4*>(rowp + ((3u ^ sw_a) << 4));
+        float4 b0, b1;
+        if (b_direct) {
+          b0 = __ldg(reinterpret_cast<const float4*>(b_direct + step * 8));
+          b1 = __ldg(reinterpret_cast<const float4*>(b_direct + step * 8) + 1);
+        } else {
+          b0 = *reinterpret_cast<const float4*>(buf + 2048 + slot_b * 32);
+          b1 = *reinterpret_cast<const float4*>(buf + 2048 + slot_b * 32 + 16);
+        }
+        tmem_wait_ld();
+        float2 x[4], m[4];
+        x[0] = add2(add2(make_float2(__uint_as_float(v[0]), __uint_as_float(v[1])), make_float2(a0.x, a0.y)), make_float2(b0.x, b0.y));
+        x[1] = add2(add2(make_float2(__uint_as_float(v[2]), __uint_as_float(v[3])), make_float2(a0.z, a0.w)), make_float2(b0.z, b0.w));
+        x[2] = add2(add2(make_float2(__uint_as_float(v[4]), __uint_as_float(v[5])), make_float2(a1.x, a1.y)), make_float2(b1.x, b1.y));
+        x[3] = add2(add2(make_float2(__uint_as_float(v[6]), __uint_as_float(v[7])), make_float2(a1.z, a1.w)), make_float2(b1.z, b1.w));
+        if (step == 0) nK = splat2(-x[0].x);
+        {
+          const float2 d0 = add2(x[0], nK), d1 = add2(x[1], nK), d2 = add2(x[2], nK), d3 = add2(x[3], nK);
+          S1p = add2(S1p, add2(d0, d2));
+          S1q = add2(S1q, add2(d1, d3));
+          Q1p = fma2(d0, d0, Q1p);
+          Q1q = fma2(d1, d1, Q1q);
+          Q1p = fma2(d2, d2, Q1p);
+          Q1q = fma2(d3, d3, Q1q);
+        }
+        m[0] = mul2(sigmoid_mufu2(x[0]), make_float2(v0.x, v0.y));
+        m[1] = mul2(sigmoid_mufu2(x[1]), make_float2(v0.z, v0.w));
+        m[2] = mul2(sigmoid_mufu2(x[2]), make_float2(v1.x, v1.y));
+        m[3] = mul2(sigmoid_mufu2(x[3]), make_float2(v1.z, v1.w));
+        if (!valid) m[0] = m[1] = m[2] = m[3] = splat2((P.agg_mode == AGG_MAX) ? -INFINITY : 0.0f);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          v[2 * j] = __float_as_uint(x[j].x);
+          v[2 * j + 1] = __float_as_uint(x[j].y);
+        }
+        tmem_st8(t_acc1 + c0, v);
+        __syncwarp();                       // every lane has read its A / V / B values: the buffer becomes the patch
+        float* patch = reinterpret_cast<float*>(buf);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {       // transposed [column][row], 36-float pitch: conflict-free
+          patch[(2 * j) * 36 + lane] = m[j].x;
+          patch[(2 * j + 1) * 36 + lane] = m[j].y;
+        }
+        __syncwarp();
+        // row-segment reduction: lane = (column = lane % 8, row group = lane / 8) sums its 8 rows of every node segment;
+        // row groups are combined with a fixed shuffle tree; seg_mask is warp-uniform; deterministic, no atomics
+        {
+          const float* pcol = patch + (lane & 7) * 36;
+          const int r_lo = (lane >> 3) * 8, r_hi = r_lo + 7;
+          const float4 t0 = *reinterpret_cast<const float4*>(pcol + r_lo);
+          const float4 t1 = *reinterpret_cast<const float4*>(pcol + r_lo + 4);
+          const float mv[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+          if (nseg == 1 && seg_mask == 0x80000000u) {   // the common case: all 32 rows belong to one node
+            float run;
+            if (P.agg_mode == AGG_MAX) {
+              run = fmaxf(fmaxf(fmaxf(mv[0], mv[1]), fmaxf(mv[2], mv[3])), fmaxf(fmaxf(mv[4], mv[5]), fmaxf(mv[6], mv[7])));
+              run = fmaxf(run, __shfl_xor_sync(0xffffffffu, run, 8));
+              run = fmaxf(run, __shfl_xor_sync(0xffffffffu, run, 16));
+            } else {
+              run = ((mv[0] + mv[1]) + (mv[2] + mv[3])) + ((mv[4] + mv[5]) + (mv[6] + mv[7]));
+              run += __shfl_xor_sync(0xffffffffu, run, 8);
+              run += __shfl_xor_sync(0xffffffffu, run, 16);
+            }
+            if (lane < 8) P.partials[(pair_base + (size_t)(my_row - first_node)) * H + c0 + lane] = run;
+          } else {
+            uint32_t mask = seg_mask;
+            int start = 0;
+            while (mask) {                         // one iteration per node segment present in this warp
+              const int end = __ffs(mask) - 1;
+              mask &= mask - 1;
+              const int lo = max(start, r_lo) - r_lo, hi = min(end, r_hi) - r_lo;   // my 8 rows of this segment
+              const uint32_t rm = (hi >= lo) ? (((2u << hi) - 1u) & ~((1u << lo) - 1u)) : 0u;
+              float run;
+              if (P.agg_mode == AGG_MAX) {
+                float r0 = -INFINITY, r1 = -INFINITY;
+#pragma unroll
+                for (int i = 0; i < 8; i += 2) {
+                  if ((rm >> i) & 1u) r0 = fmaxf(r0, mv[i]);
+                  if ((rm >> (i + 1)) & 1u) r1 = fmaxf(r1, mv[i + 1]);
+                }
+                run = fmaxf(r0, r1);
+                run = fmaxf(run, __shfl_xor_sync(0xffffffffu, run, 8));
+                run = fmaxf(run, __shfl_xor_sync(0xffffffffu, run, 16));
+              } else {
+                float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; i += 4) {
+                  if ((rm >> i) & 1u) r0 += mv[i];
+                  if ((rm >> (i + 1)) & 1u) r1 += mv[i + 1];
+                  if ((rm >> (i + 2)) & 1u) r2 += mv[i + 2];
+                  if ((rm >> (i + 3)) & 1u) r3 += mv[i + 3];
+                }
+                run = (r0 + r1) + (r2 + r3);
+                run += __shfl_xor_sync(0xffffffffu, run, 8);
+                run += __shfl_xor_sync(0xffffffffu, run, 16);
+              }
+              const int node = __shfl_sync(0xffffffffu, my_row, end);
+              if (lane < 8) P.partials[(pair_base + (size_t)(node - first_node)) * H + c0 + lane] = run;
+              start = end + 1;
+            }
+          }
+        }
+        __syncwarp();                       // patch may be overwritten by the next gather
+        if (step + 2 < 8) gather_issue(step + 2, buf);
+      }
+      const float K1 = -nK.x, S1 = (S1p.x + S1p.y) + (S1q.x + S1q.y), Q1 = (Q1p.x + Q1p.y) + (Q1q.x + Q1q.y);
+      tmem_wait_st();
+      // LayerNorm statistics of the four column parts of a row are exchanged through the (idle) gather buffers
+      float mean1, rstd1;
+      {
+        float* sb = reinterpret_cast<float*>(gbuf0);
+        sb[lane] = K1;
+        sb[32 + lane] = S1;
+        sb[64 + lane] = Q1;
+        worker_bar();
+        if (lane == 0) mbar_arrive(&idx_free[it & 1]);   // endpoints of this tile are no longer read
+        float kk[4], sp[4], qp[4];
+        float msum = 0.f;
+#pragma unroll
+        for (int p2 = 0; p2 < 4; ++p2) {
+          const float* pp = stat_buf(p2);
+          kk[p2] = pp[lane]; sp[p2] = pp[32 + lane]; qp[p2] = pp[64 + lane];
+          msum += kk[p2] * 64.0f + sp[p2];
+        }
+        mean1 = msum * (1.0f / H);
+        float ss = 0.f;   // sum (x - mean)^2 = sum_p [Q_p - 2 (mean - K_p) S_p + n_p (mean - K_p)^2]
+#pragma unroll
+        for (int p2 = 0; p2 < 4; ++p2) {
+          const float dk = mean1 - kk[p2];
+          ss += qp[p2] - 2.0f * dk * sp[p2] + 64.0f * dk * dk;
+        }
+        rstd1 = rsqrtf(fmaxf(ss * (1.0f / H), 0.0f) + LN_EPS);
+      }
+      PHASE(2);   // E1
+      // ================= E2: e_til = relu(LN_e(e_hat)) + tau, statistics for LN_O =================
+      float S2, Q2;
+      {
+        const float2 rs = splat2(rstd1), nm = splat2(-mean1 * rstd1);
+        float2 S2p = splat2(0.f), Q2p = splat2(0.f);
+#pragma unroll 1
+        for (int c0 = cbase; c0 < cbase + 64; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(t_acc1 + c0, v);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 g4 = *reinterpret_cast<const float4*>(prm + c0 + 4 * j);
+            const float4 b4 = *reinterpret_cast<const float4*>(prm + H + c0 + 4 * j);
+            const float4 t4 = *reinterpret_cast<const float4*>(prm + 2 * H + c0 + 4 * j);
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              const float2 xx = make_float2(__uint_as_float(v[4 * j + 2 * hh]), __uint_as_float(v[4 * j + 2 * hh + 1]));
+              const float2 gg = hh ? make_float2(g4.z, g4.w) : make_float2(g4.x, g4.y);
+              const float2 bb2 = hh ? make_float2(b4.z, b4.w) : make_float2(b4.x, b4.y);
+              const float2 tt = hh ? make_float2(t4.z, t4.w) : make_float2(t4.x, t4.y);
+              float2 y = fma2(fma2(xx, rs, nm), gg, bb2);          // LN_e affine
+              y = add2(make_float2(fmaxf(y.x, 0.0f), fmaxf(y.y, 0.0f)), tt);   // ReLU + time vector
+              S2p = add2(S2p, y);
+              Q2p = fma2(y, y, Q2p);
+              v[4 * j + 2 * hh] = __float_as_uint(y.x);
+              v[4 * j + 2 * hh + 1] = __float_as_uint(y.y);
+            }
+          }
+          tmem_st16(t_acc1 + c0, v);
+        }
+        S2 = S2p.x + S2p.y;
+        Q2 = Q2p.x + Q2p.y;
+      }
+      tmem_wait_st();
+      {
+        float* sb = reinterpret_cast<float*>(gbuf0);
+        sb[128 + lane] = S2;
+        sb[160 + lane] = Q2;
+        worker_bar();   // also: every part's e_til is in TMEM before E3 reads columns written by other warps
+        S2 = 0.f;
+        Q2 = 0.f;
+#pragma unroll
+        for (int p2 = 0; p2 < 4; ++p2) {
+          const float* pp = stat_buf(p2);
+          S2 += pp[128 + lane];
+          Q2 += pp[160 + lane];
+        }
+      }
+      const float mean2 = S2 * (1.0f / H);
+      const float var2 = fmaxf(Q2 * (1.0f / H) - mean2 * mean2, 0.0f);
+      const float rstd2 = rsqrtf(var2 + LN_EPS);
+      const float2 rs2 = splat2(rstd2), nm2 = splat2(-mean2 * rstd2);
+      PHASE(3);   // E2
+      // ================= E3: s = silu(LN_O(e_til)) -> GEMM2 A operand, in place in TMEM =================
+      // every 64-column K-chunk is produced cooperatively (part p converts columns [64 kc + 16 p, +16)), so chunk 0 is
+      // complete after a quarter of E3 and GEMM2 runs underneath the rest
+#pragma unroll 1
+      for (int kc = 0; kc < 4; ++kc) {
+        const int c0 = kc * 64 + part * 16;
+        uint32_t v[16], w16[16];
+        tmem_ld16(t_acc1 + c0, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {               // 8 elements each
+          float z[8];
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int e0 = 8 * j + 4 * hh;
+            const float4 g4 = *reinterpret_cast<const float4*>(prm + 3 * H + c0 + e0);
+            const float4 b4 = *reinterpret_cast<const float4*>(prm + 4 * H + c0 + e0);
+            const float2 t01 = fma2(fma2(make_float2(__uint_as_float(v[e0]), __uint_as_float(v[e0 + 1])), rs2, nm2),
+                                    make_float2(g4.x, g4.y), make_float2(b4.x, b4.y));
+            const float2 t23 = fma2(fma2(make_float2(__uint_as_float(v[e0 + 2]), __uint_as_float(v[e0 + 3])), rs2, nm2),
+                                    make_float2(g4.z, g4.w), make_float2(b4.z, b4.w));
+            const float2 s01 = mul2(t01, sigmoid_mufu2(t01)), s23 = mul2(t23, sigmoid_mufu2(t23));   // SiLU
+            z[4 * hh] = s01.x; z[4 * hh + 1] = s01.y; z[4 * hh + 2] = s23.x; z[4 * hh + 3] = s23.y;
+          }
+          uint2 h0, l0, h1, l1;
+          split4(make_float4(z[0], z[1], z[2], z[3]), h0, l0);
+          split4(make_float4(z[4], z[5], z[6], z[7]), h1, l1);
+          w16[4 * j] = h0.x; w16[4 * j + 1] = h0.y; w16[4 * j + 2] = h1.x; w16[4 * j + 3] = h1.y;             // hi: columns 0..7
+          w16[8 + 4 * j] = l0.x; w16[8 + 4 * j + 1] = l0.y; w16[8 + 4 * j + 2] = l1.x; w16[8 + 4 * j + 3] = l1.y;   // lo: columns 8..15
+        }
+        tmem_st16(t_acc1 + c0, w16);
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(&a2_full[kc]);
+      }
+      PHASE(4);   // E3
+    }
+#ifdef DFB_PHASE_PROF
+    if (prof)
+      for (int i = 0; i < 8; ++i) atomicAdd(P.phase_cycles + i, (unsigned long long)pc[i]);
+#endif
+#undef PHASE
+  }
+
+  // teardown: nobody may leave while the peer can still signal this CTA's barriers or read its shared memory
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------------------
+struct State {
+  bool ready = false;
+  CUtensorMap wmap;   // bf16 weight arena, box 32 K x 128 rows, 64B swizzle
+  int max_clusters = 0;
+};
+
+inline int init(State* st, TcState* tc) {
+  cudaError_t e = cudaFuncSetAttribute(k_edge_layer_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  if (e != cudaSuccess) {
+    tc->err = std::string("cudaFuncSetAttribute(pair kernel): ") + cudaGetErrorString(e);
+    return -2;
+  }
+  st->max_clusters = tc->num_sms / 2;
+  return 0;
+}
+
+inline int bind_weights(State* st, TcState* tc, const void* arena, int L) {
+  cuuint64_t gdim[2] = {(cuuint64_t)H, (cuuint64_t)(L * 12 + 4) * H};
+  cuuint64_t gstride[1] = {(cuuint64_t)H * sizeof(uint16_t)};
+  cuuint32_t box[2] = {32u, 128u};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = ((PFN_encodeTiled)tc->encode_fn)(&st->wmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(arena), gdim,
+                                                gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    tc->err = "cuTensorMapEncodeTiled(weights, 64B swizzle) failed with CUresult " + std::to_string((int)r);
+    return -2;
+  }
+  st->ready = true;
+  return 0;
+}
+
+// One fused middle layer (reads and writes e): l >= 1 for TSP, any layer with write_e for MIS except layer 0.
+inline int launch(State* st, TcState* tc, int l, float* e, const float* uvab, float* partials, GraphDev g, LayerParams lp,
+                  const float* tvec_edge, int agg_mode, cudaStream_t stream) {
+  tc->last_launches = 0;
+  if (!st->ready) {
+    tc->err = "pair kernel: weights not bound";
+    return -1;
+  }
+  int r = tc_ensure_emap(tc, e, g.E);
+  if (r) return r;
+  Params P;
+  P.e = e; P.uvab = uvab; P.partials = partials; P.g = g; P.lp = lp; P.tvec = tvec_edge;
+  P.debug_acc = tc->debug_acc; P.error_flag = tc->error_flag; P.phase_cycles = tc->phase_cycles;
+  P.agg_mode = agg_mode; P.w_row_base = l * 12 * H;
+  P.n_tiles = (g.E + TC_TILE - 1) / TC_TILE;
+  P.probe = tc->probe;
+  const int n_pairs = (P.n_tiles + 1) / 2;
+  const int clusters = n_pairs < st->max_clusters ? n_pairs : st->max_clusters;
+  k_edge_layer_pair<<<2 * clusters, THREADS, SMEM_BYTES, stream>>>(st->wmap, tc->emap, P);
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) {
+    tc->err = std::string("pair kernel launch: ") + cudaGetErrorString(err);
+    return -2;
+  }
+  tc->last_launches = 1;
+  return 0;
+}
+
+}  // namespace v2
+}  // namespace dfb

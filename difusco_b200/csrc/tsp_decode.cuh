@@ -329,11 +329,11 @@ __global__ void __launch_bounds__(256) k_twoopt_eval(const double* __restrict__ 
 // own arg-min whenever the batch minimum passes the threshold), refresh dnext.
 __global__ void __launch_bounds__(1024) k_twoopt_apply(long long* __restrict__ tours, double* __restrict__ pos,
                                                        double* __restrict__ dnext, const TwoOptCand* __restrict__ cand,
-                                                       TwoOptState* __restrict__ state, int N, int B, int ntiles,
-                                                       long long max_iterations) {
+                                                       TwoOptState* __restrict__ state, TwoOptCand* __restrict__ s_best,
+                                                       int N, int B, int ntiles, long long max_iterations) {
   if (state->done) return;
   __shared__ TwoOptCand s_red[32];
-  __shared__ TwoOptCand s_best[64];   // per tour (B <= 64)
+  // s_best: per-tour arg-min in global memory (any batch size; written by thread 0, read after __syncthreads)
   const int tid = threadIdx.x;
   for (int b = 0; b < B; ++b) {
     double best = 0.0;

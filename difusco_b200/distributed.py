@@ -39,16 +39,26 @@ def gather_heatmaps(local, sizes=None, group=None):
   return [o[:s] for o, s in zip(out, sizes)]
 
 
-def denoise_sharded(instances, run_batch, rank=None, world=None, batch=16, group=None):
+def denoise_sharded(instances, run_batch, rank=None, world=None, batch=16, group=None, device=None,
+                    dtype=torch.float32):
   """Round of instance-parallel inference.
 
   instances: list of problem descriptions (anything `run_batch` understands), identical on all ranks.
   run_batch(list_of_instances) -> 1-D float tensor: concatenated heatmaps of that block-diagonal batch.
   Every rank processes its contiguous shard in batches of `batch`; returns, on every rank, the list of
-  per-rank concatenated heatmaps (rank order == instance order)."""
+  per-rank concatenated heatmaps (rank order == instance order).
+  device / dtype: where an EMPTY shard (more ranks than instances) lives; every rank must join the collectives with a
+  tensor of the backend's device (CUDA for nccl) and of the same dtype as the other ranks' heatmaps.  Default device:
+  the current CUDA device under nccl, the CPU otherwise."""
   rank = dist.get_rank(group) if rank is None else rank
   world = dist.get_world_size(group) if world is None else world
   lo, hi = shard_range(len(instances), rank, world)
   outs = [run_batch(instances[i:min(i + batch, hi)]) for i in range(lo, hi, batch)]
-  local = torch.cat(outs) if outs else torch.zeros(0)
+  if outs:
+    local = torch.cat(outs)
+  else:
+    if device is None:
+      nccl = dist.is_initialized() and dist.get_backend(group) == "nccl"
+      device = torch.device("cuda", torch.cuda.current_device()) if nccl else torch.device("cpu")
+    local = torch.zeros(0, device=device, dtype=dtype)
   return gather_heatmaps(local, group=group)

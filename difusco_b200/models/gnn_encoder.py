@@ -14,8 +14,9 @@ Interface notes (reference behaviour kept):
     evaluated as the row-major complete graph incl. self pairs (gnn_encoder.py:365 makes the
     graph all-ones), GroupNorm per sample.
   * dense + node_feature_only raises NotImplementedError (:457), as in the reference.
-Only inference is in scope: per-edge timestep vectors (training, pl_tsp_model.py:66-68) and
-autograd are not supported and raise.
+Only inference is in scope: per-edge timestep vectors (training, pl_tsp_model.py:66-68) raise
+NotImplementedError; autograd is not supported - outputs carry no grad_fn, and a call with grad mode
+enabled on parameters that require grad warns once.
 """
 import math
 
@@ -60,6 +61,8 @@ class GNNLayer(nn.Module):
 
 
 class GNNEncoder(nn.Module):
+  _warned_no_grad = False
+
   def __init__(self, n_layers, hidden_dim, out_channels=1, aggregation="sum", norm="layer",
                learn_norm=True, track_norm=False, gated=True,
                sparse=False, use_activation_checkpoint=False, node_feature_only=False,
@@ -109,6 +112,7 @@ class GNNEncoder(nn.Module):
     idx = dev.index if dev.index is not None else torch.cuda.current_device()
     if self._ctx is None or self._ctx.device != idx:
       self._ctx = _cabi.Context(idx)
+      _cabi.device_context(idx, prefer=self._ctx)   # k-NN / 2-opt helpers share the first model's context
       self._ctx.set_aggregation(self.aggregation)
       self._weights_key = self._graph_key = self._points_key = None
     self._sync_weights()
@@ -208,9 +212,12 @@ class GNNEncoder(nn.Module):
     return out
 
   def forward(self, x, timesteps, graph=None, edge_index=None):
-    if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-      # inference engine: never builds an autograd graph; make misuse visible
-      pass
+    if torch.is_grad_enabled() and not GNNEncoder._warned_no_grad and any(p.requires_grad for p in self.parameters()):
+      # inference engine: never builds an autograd graph; make misuse visible (once)
+      import warnings
+      warnings.warn("difusco_b200.GNNEncoder is an inference engine: outputs carry no grad_fn "
+                    "(call it under torch.no_grad(); training is outside this package's scope)")
+      GNNEncoder._warned_no_grad = True
     if self.node_feature_only:
       if self.sparse:
         return self.sparse_forward_node_feature_only(x, timesteps, edge_index)

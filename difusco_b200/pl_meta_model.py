@@ -157,7 +157,9 @@ class COMetaModel(_Base):
     else:
       draws = torch.randn(n, device=dev, dtype=torch.float32) if consts[3] != 0.0 else None
       if consts[3] == 0.0 and t <= 1:
-        torch.randn(1, device=dev)   # the reference draws randn_like even when its coefficient is 0 (:164)
+        # the reference draws randn_like(xt) here even though its coefficient is 0 (:164): draw the same number of
+        # elements so that torch's generator offset advances exactly as in the reference
+        torch.randn(n, device=dev, dtype=torch.float32)
       mode = _cabi.GAUSSIAN
     self._step_counter += 1
     ctx.denoise_step(mode, xin.data_ptr(), float(t), consts, last, draws.data_ptr() if draws is not None else None,

@@ -20,18 +20,13 @@ import scipy.sparse
 
 from .. import _cabi
 
-_ENGINES = {}
-
-
 def _engine(device):
   import torch
   dev = torch.device(device)
   if dev.type != "cuda":
     raise RuntimeError("difusco_b200.batched_two_opt_torch runs on a CUDA device only (no CPU fallback)")
   idx = dev.index if dev.index is not None else torch.cuda.current_device()
-  if idx not in _ENGINES:
-    _ENGINES[idx] = _cabi.Context(idx)
-  return _ENGINES[idx]
+  return _cabi.device_context(idx)   # shared with the model and the k-NN builder: one dfb_ctx per GPU
 
 
 def batched_two_opt_torch(points, tour, max_iterations=1000, device="cuda"):
@@ -80,9 +75,14 @@ def merge_tours(adj_mat, np_points, edge_index_np, sparse_graph=False, parallel_
       edge_index, heat = np.asarray(edge_index_np), part.reshape(-1)
     else:                         # adj_mat[0] + adj_mat[0].T  ==  both orientations of the complete graph
       edge_index, heat = _complete_graph(n), part[0].reshape(-1)
-    status, tour, it = _cabi.tsp_merge_sparse(pts64, heat, edge_index, mode=0 if exact else 1)
+    if heat.dtype != np.float32 and exact:
+      # the reference builds its keys in the caller's dtype; a float64 heat map can order edges differently from its
+      # float32 rounding, so it takes the reference's own dense formulation instead of the float32 sparse path
+      status = _cabi.MERGE_INCOMPLETE
+    else:
+      status, tour, it = _cabi.tsp_merge_sparse(pts64, heat, edge_index, mode=0 if exact else 1)
     if status != _cabi.MERGE_COMPLETE:
-      tour, it = _cabi.tsp_merge_order(n, _dense_order(points, heat.astype(np.float32, copy=False), edge_index))
+      tour, it = _cabi.tsp_merge_order(n, _dense_order(points, heat, edge_index))
     tours.append([int(v) for v in tour])
     iterations.append(it)
   return tours, np.mean(iterations)

@@ -30,7 +30,8 @@ enum {
 
 enum { DFB_TASK_TSP = 0, DFB_TASK_MIS = 1 };               /* pl_tsp_model.py / pl_mis_model.py          */
 enum { DFB_DIFFUSION_CATEGORICAL = 0, DFB_DIFFUSION_GAUSSIAN = 1 }; /* pl_meta_model.py:27-36           */
-enum { DFB_EDGE_IMPL_TC = 0, DFB_EDGE_IMPL_FP32 = 1 };     /* tcgen05 product kernel / fp32 validation kernel */
+enum { DFB_EDGE_IMPL_TC = 0, DFB_EDGE_IMPL_FP32 = 1, DFB_EDGE_IMPL_TC1 = 2 }; /* tcgen05 product path (CTA-pair kernel on the
+  middle layers) / fp32 validation kernel / the single-CTA tcgen05 kernel on every layer (A/B and validation) */
 
 typedef struct dfb_ctx dfb_ctx;
 
@@ -162,7 +163,8 @@ int dfb_profile_end(dfb_ctx* ctx, double* edge_kernel_ms, int64_t* edge_kernel_l
  * acc_out (E,256).  DEVICE pointers.  Used by the parity tests to localise failures. */
 int dfb_debug_edge_gemm(dfb_ctx* ctx, int layer, const float* e_in, float* acc_out, void* stream);
 
-/* Tuning hook: per-phase cycle counters of the tcgen05 edge kernel (DFB_TC_PROBE bit 7); out[8], host. */
+/* Tuning hook: per-phase cycle counters of the tcgen05 edge kernels (DFB_TC_PROBE bit 7, --prof build); out must hold
+ * 16 unsigned 64-bit values (host): [0..7] phases, [8..15] E1 sub-phases of the single-CTA kernel.  Read-and-reset. */
 int dfb_debug_phase_cycles(dfb_ctx* ctx, unsigned long long* out);
 
 /* Diagnostic: watchdog record of the tcgen05 kernel's bounded barrier waits (host-mapped memory, readable after a

@@ -22,8 +22,15 @@ import torch
 REFERENCE_ROOT = "/root/reference/difusco"
 
 
-def install():
+def install(root=None):
+  """root: directory holding the reference's `difusco/` sources (default /root/reference/difusco; bench.py passes
+  oracle/_ref/difusco, the byte-for-byte copy that travels to the GPU box)."""
+  global REFERENCE_ROOT
+  if root is not None:
+    REFERENCE_ROOT = root
   if "torch_sparse" in sys.modules and getattr(sys.modules["torch_sparse"], "_dfb_shim", False):
+    if REFERENCE_ROOT not in sys.path:
+      sys.path.insert(0, REFERENCE_ROOT)
     return
 
   ts = types.ModuleType("torch_sparse")

@@ -9,9 +9,9 @@ from difusco_b200.models.gnn_encoder import GNNEncoder
 from difusco_b200.pl_mis_model import MISModel
 from difusco_b200.pl_tsp_model import TSPModel
 
-IMPLS = {"tc": _cabi.EDGE_IMPL_TC, "fp32": _cabi.EDGE_IMPL_FP32}
+IMPLS = {"tc": _cabi.EDGE_IMPL_TC, "fp32": _cabi.EDGE_IMPL_FP32, "tc1": _cabi.EDGE_IMPL_TC1}
 # fp32 validation kernel: fp32 reassociation only.  tcgen05 kernel: 3-term bf16 split (~2^-17 per product).
-TOL = {"fp32": 2e-5, "tc": 1e-4}
+TOL = {"fp32": 2e-5, "tc": 1e-4, "tc1": 1e-4}
 
 
 def args(**kw):

@@ -61,6 +61,8 @@ def test_sparse_item_layout_matches_reference_semantics():
     ds = TSPGraphDataset(_write(tmp, pts, tours), sparse_factor=k)
     idx, graph, pind, eind, tour = ds[0]
   assert pind.tolist() == [n] and eind.tolist() == [n * k] and graph.x.dtype == torch.float32
+  # the item is made of CPU tensors like the reference's (DataLoader pin_memory / the model's own .to(device) work)
+  assert graph.edge_index.device.type == "cpu" and graph.edge_attr.device.type == "cpu" and graph.x.device.type == "cpu"
   _, ref = KDTree(pts[0], leaf_size=30, metric="euclidean").query(pts[0], k=k, return_distance=True)
   assert np.array_equal(graph.edge_index[1].cpu().numpy().reshape(n, k), ref)
   succ = np.zeros(n, dtype=np.int64)

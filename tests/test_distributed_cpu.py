@@ -52,6 +52,9 @@ def _worker(rank, world, port, q):
     mine = run_batch(inst[lo:hi]) if hi > lo else torch.zeros(0)
     sizes = [sum(b["E"] for b in inst[slice(*shard_range(5, r, world))]) for r in range(world)]
     ok = ok and torch.equal(torch.cat(gather_heatmaps(mine, sizes=sizes)), ref)
+    # more ranks than instances: the rank with the empty shard still joins the collectives (device / dtype explicit)
+    one = denoise_sharded(inst[:1], run_batch, batch=2, device=torch.device("cpu"), dtype=torch.float32)
+    ok = ok and len(one) == world and torch.equal(torch.cat(one), run_batch(inst[:1])) and one[-1].dtype == torch.float32
     q.put((rank, bool(ok)))
   finally:
     dist.destroy_process_group()

@@ -15,9 +15,10 @@ pytestmark = pytest.mark.gpu
 # ------------------------------------------------------------------------------------------------
 # building block: split-bf16 GEMM on tcgen05 (descriptors, TMA, TMEM plumbing)
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("E", [128, 1000, 128 * 150 + 17])
-def test_tc_gemm_matches_fp64_matmul(weights2, E):
-  enc = G.encoder(weights2, 2)
+@pytest.mark.parametrize("impl", ["tc", "tc1"])
+@pytest.mark.parametrize("E", [128, 1000, 128 * 150 + 17, 128 * 301])
+def test_tc_gemm_matches_fp64_matmul(weights2, E, impl):
+  enc = G.encoder(weights2, 2, impl=impl)
   V = 64
   rng = np.random.default_rng(E)
   ei = np.stack([np.sort(rng.integers(0, V, E)), rng.integers(0, V, E)]).astype(np.int64)
