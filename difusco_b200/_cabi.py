@@ -19,7 +19,7 @@ SYMBOLS = [
     "dfb_set_edge_impl", "dfb_load_weights", "dfb_prepare_graph", "dfb_set_points",
     "dfb_encoder_forward", "dfb_denoise_step", "dfb_denoise", "dfb_denoise_host",
     "dfb_launch_count", "dfb_profile_begin", "dfb_profile_end", "dfb_debug_edge_gemm",
-    "dfb_debug_phase_cycles", "dfb_debug_watchdog", "dfb_knn_graph",
+    "dfb_debug_phase_cycles", "dfb_debug_watchdog", "dfb_knn_graph", "dfb_set_graph_capture",
     "dfb_tsp_merge_sparse", "dfb_tsp_merge_order", "dfb_two_opt", "dfb_write_heatmap_txt",
 ]
 
@@ -60,6 +60,7 @@ def lib():
   L.dfb_debug_edge_gemm.argtypes = [vp, i32, vp, vp, vp]
   L.dfb_debug_phase_cycles.argtypes = [vp, C.POINTER(C.c_uint64)]
   L.dfb_debug_watchdog.argtypes = [vp, C.POINTER(C.c_int)]
+  L.dfb_set_graph_capture.argtypes = [vp, i32]
   L.dfb_knn_graph.argtypes = [vp, vp, i64, i32, i64, vp, vp]
   L.dfb_tsp_merge_sparse.argtypes = [vp, i64, vp, vp, i64, i32, vp, C.POINTER(i64)]
   L.dfb_tsp_merge_order.argtypes = [i64, vp, i64, vp, C.POINTER(i64)]
@@ -257,13 +258,16 @@ class Context(object):
     self._ck(lib().dfb_profile_end(self._h, C.byref(ms), C.byref(n)))
     return ms.value, n.value
 
+  def set_graph_capture(self, enabled):
+    self._ck(lib().dfb_set_graph_capture(self._h, int(bool(enabled))))
+
   def debug_watchdog(self):
     out = (C.c_int * 4)()
     lib().dfb_debug_watchdog(self._h, out)
     return [int(x) for x in out]
 
   def debug_phase_cycles(self):
-    out = (C.c_uint64 * 16)()
+    out = (C.c_uint64 * 32)()
     self._ck(lib().dfb_debug_phase_cycles(self._h, out))
     return [int(x) for x in out]
 

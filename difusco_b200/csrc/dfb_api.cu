@@ -47,11 +47,39 @@ struct dfb_ctx {
   bool graph_ready = false, points_ready = false;
   GraphDev g{};
   int gn_segments = 1;
+  int max_seg = 0;   // most node segments inside one 32-edge group (pair kernel handles up to v2::MAXSEG)
   DevBuf d_row, d_col, d_perm, d_rowptr, d_grp_first, d_grp_pair, d_ei_stage;
   // ---- workspace ----
   DevBuf e, h, h0, uvab, uvab0, partials, feat, tvec, tvals, gn_part, gn_stats, d_points, d_xt, d_u;
   DevBuf opt_points, opt_tours, opt_pos, opt_dnext, opt_cand, opt_tiles, opt_state, opt_best;   // 2-opt (row f3)
   int tvec_steps_cap = 0;
+  // ---- step staging (pinned) + captured loop ----
+  // dfb_denoise_step / dfb_denoise never allocate, never synchronise the host with the stream and never touch the
+  // heap after the first call of a shape: timesteps and posterior constants go through two pinned staging slots
+  // (guarded by an event each), the per-step table lives in device memory, and the whole loop is replayed as ONE
+  // CUDA graph that is re-captured only when the shape / buffers / implementation change.
+  static constexpr int STAGE_SLOTS = 2, MAX_STEPS = 4096;
+  float* h_tvals[STAGE_SLOTS] = {nullptr, nullptr};
+  StepParams* h_steps[STAGE_SLOTS] = {nullptr, nullptr};
+  cudaEvent_t stage_ev[STAGE_SLOTS] = {nullptr, nullptr};
+  int stage_next = 0;
+  DevBuf d_steps;
+  uint64_t buf_gen = 0;          // bumped whenever a device buffer is (re)allocated or the graph / weights change
+  bool capture_enabled = true;
+  bool capture_broken = false;
+  cudaGraphExec_t loop_exec = nullptr;
+  cudaStream_t loop_stream = nullptr;   // the captured loop runs on the library's own stream (the caller's may be the
+  cudaEvent_t loop_in = nullptr, loop_out = nullptr;   // legacy default stream, which cannot be captured), fenced by events
+  struct LoopKey {
+    uint64_t buf_gen = ~0ull;
+    int steps = 0, diffusion = 0, impl = 0, agg = 0, pair = 0;
+    const void* uniforms = nullptr;
+    bool operator==(const LoopKey& o) const {
+      return buf_gen == o.buf_gen && steps == o.steps && diffusion == o.diffusion && impl == o.impl && agg == o.agg &&
+             pair == o.pair && uniforms == o.uniforms;
+    }
+  } loop_key;
+  int64_t loop_launches = 0;     // kernel launches inside one replay of the captured loop
   // ---- accounting ----
   int64_t launches = 0;
   bool profiling = false;
@@ -59,7 +87,7 @@ struct dfb_ctx {
   size_t ev_used = 0;
   TcState tc;
   v2::State pair;   // round-2 CTA-pair kernel (middle layers of the product path)
-  bool pair_enabled = false;   // bring-up switch (DFB_PAIR_KERNEL=1) until the pair kernel is parity-green on the GPU
+  bool pair_enabled = true;    // DFB_PAIR_KERNEL=0 routes every layer to the single-CTA kernel (A/B timing)
 };
 
 #define FAIL(ctx, code, ...)                         \
@@ -87,6 +115,7 @@ struct dfb_ctx {
 
 static int ensure(dfb_ctx* ctx, DevBuf& b, size_t bytes) {
   if (bytes <= b.cap) return DFB_OK;
+  ctx->buf_gen++;   // a captured loop that baked the old pointer is stale
   if (b.p) cudaFree(b.p);
   b.p = nullptr;
   b.cap = 0;
@@ -167,9 +196,29 @@ extern "C" int dfb_create(dfb_ctx** out, int device) {
     delete ctx;
     return DFB_E_CUDA;
   }
+  for (int i = 0; i < dfb_ctx::STAGE_SLOTS; ++i) {
+    if ((e = cudaHostAlloc((void**)&ctx->h_tvals[i], dfb_ctx::MAX_STEPS * sizeof(float), cudaHostAllocDefault)) != cudaSuccess ||
+        (e = cudaHostAlloc((void**)&ctx->h_steps[i], dfb_ctx::MAX_STEPS * sizeof(StepParams), cudaHostAllocDefault)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&ctx->stage_ev[i], cudaEventDisableTiming)) != cudaSuccess) {
+      g_create_error = std::string("pinned staging: ") + cudaGetErrorString(e);
+      delete ctx;
+      return DFB_E_CUDA;
+    }
+  }
+  if ((e = cudaStreamCreateWithFlags(&ctx->loop_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&ctx->loop_in, cudaEventDisableTiming)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&ctx->loop_out, cudaEventDisableTiming)) != cudaSuccess) {
+    g_create_error = std::string("loop stream: ") + cudaGetErrorString(e);
+    delete ctx;
+    return DFB_E_CUDA;
+  }
+  {
+    const char* cg = getenv("DFB_GRAPH_CAPTURE");
+    if (cg && atoi(cg) == 0) ctx->capture_enabled = false;
+  }
   {
     const char* pk = getenv("DFB_PAIR_KERNEL");
-    ctx->pair_enabled = pk && atoi(pk) != 0;
+    if (pk) ctx->pair_enabled = atoi(pk) != 0;
   }
   r = v2::init(&ctx->pair, &ctx->tc);
   if (r != 0) {
@@ -192,6 +241,16 @@ extern "C" int dfb_destroy(dfb_ctx* ctx) {
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   for (cudaEvent_t ev : ctx->ev_pool) cudaEventDestroy(ev);
+  if (ctx->loop_exec) cudaGraphExecDestroy(ctx->loop_exec);
+  if (ctx->loop_stream) cudaStreamDestroy(ctx->loop_stream);
+  if (ctx->loop_in) cudaEventDestroy(ctx->loop_in);
+  if (ctx->loop_out) cudaEventDestroy(ctx->loop_out);
+  if (ctx->d_steps.p) cudaFree(ctx->d_steps.p);
+  for (int i = 0; i < dfb_ctx::STAGE_SLOTS; ++i) {
+    if (ctx->h_tvals[i]) cudaFreeHost(ctx->h_tvals[i]);
+    if (ctx->h_steps[i]) cudaFreeHost(ctx->h_steps[i]);
+    if (ctx->stage_ev[i]) cudaEventDestroy(ctx->stage_ev[i]);
+  }
   tc_destroy(&ctx->tc);
   delete ctx;
   return DFB_OK;
@@ -416,6 +475,7 @@ extern "C" int dfb_load_weights(dfb_ctx* ctx, int n_layers, int hidden_dim, int 
     CK(ctx, cudaDeviceSynchronize());
   }
   ctx->weights_loaded = true;
+  ctx->buf_gen++;
   ctx->points_ready = false;
   return DFB_OK;
 }
@@ -482,13 +542,17 @@ extern "C" int dfb_prepare_graph(dfb_ctx* ctx, const int64_t* edge_index, int64_
   }
   const int nG = (E + GROUP - 1) / GROUP;
   std::vector<int> gfirst(nG), gpair((size_t)nG + 1);
-  int np = 0;
+  int np = 0, max_seg = 0;
   for (int gI = 0; gI < nG; ++gI) {
     int s0 = gI * GROUP, s1 = std::min(E, s0 + GROUP) - 1;
     gfirst[gI] = row[s0];
     gpair[gI] = np;
     np += row[s1] - row[s0] + 1;
+    int segs = 1;
+    for (int q = s0 + 1; q <= s1; ++q) segs += row[q] != row[q - 1];
+    max_seg = std::max(max_seg, segs);
   }
+  ctx->max_seg = max_seg;
   gpair[nG] = np;
 
   ENS(ctx, ctx->d_row, (size_t)E * 4);
@@ -518,6 +582,9 @@ extern "C" int dfb_prepare_graph(dfb_ctx* ctx, const int64_t* edge_index, int64_
   // workspace
   const size_t Epad = (size_t)((E + 127) / 128) * 128;   // whole 128-row tiles for the tensor-core kernel
   ENS(ctx, ctx->e, Epad * H * sizeof(float));
+  // the padding rows of the last tile are carried through every layer like real rows (and discarded): they must start
+  // finite, or a stale NaN would travel with them
+  if (Epad > (size_t)E) CK(ctx, cudaMemsetAsync((float*)ctx->e.p + (size_t)E * H, 0, (Epad - E) * H * sizeof(float), st));
   ENS(ctx, ctx->h, (size_t)V * H * sizeof(float));
   ENS(ctx, ctx->h0, (size_t)V * H * sizeof(float));
   ENS(ctx, ctx->uvab, (size_t)V * 4 * H * sizeof(float));
@@ -529,11 +596,12 @@ extern "C" int dfb_prepare_graph(dfb_ctx* ctx, const int64_t* edge_index, int64_
     int R = ctx->node_only ? V : E;
     int rps = R / gn_segments;
     int bps = (rps + GN_ROWS_PER_BLOCK - 1) / GN_ROWS_PER_BLOCK;
-    ENS(ctx, ctx->gn_part, (size_t)gn_segments * bps * 32 * 2 * sizeof(double));
+    ENS(ctx, ctx->gn_part, std::max((size_t)gn_segments * bps, (size_t)1024) * 32 * 2 * sizeof(double));
     ENS(ctx, ctx->gn_stats, (size_t)gn_segments * 32 * 2 * sizeof(float));
   }
   ENS(ctx, ctx->d_xt, (size_t)std::max(V, E) * sizeof(float));
   ctx->graph_ready = true;
+  ctx->buf_gen++;
   ctx->points_ready = false;
   return DFB_OK;
 }
@@ -604,8 +672,10 @@ extern "C" int dfb_set_points(dfb_ctx* ctx, const float* points, void* stream_) 
 // ================================================================================================
 // one forward (+ optional fused posterior)
 // ================================================================================================
+// gn_blocks: when non-null and the pair kernel runs this layer, it also produces the head's GroupNorm partial sums
+// (ctx->gn_part) and *gn_blocks receives the number of partial blocks; otherwise *gn_blocks stays 0.
 static int launch_edge_layer(dfb_ctx* ctx, int l, const float* uvab, const float* tvec_edge, int write_e,
-                             int e_zero, const float* xt_for_lut, cudaStream_t st) {
+                             int e_zero, const float* xt_for_lut, cudaStream_t st, int* gn_blocks = nullptr) {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   if (ctx->profiling) {
     if (ctx->ev_used + 2 > ctx->ev_pool.size()) {
@@ -629,10 +699,10 @@ static int launch_edge_layer(dfb_ctx* ctx, int l, const float* uvab, const float
                                                             ctx->g, ctx->layers[l], tvec_edge, write_e,
                                                             ctx->agg_mode);
     CKL(ctx);
-  } else if (ctx->edge_impl == DFB_EDGE_IMPL_TC && ctx->pair_enabled && write_e && !e_zero && !xt_for_lut) {
+  } else if (ctx->edge_impl == DFB_EDGE_IMPL_TC && ctx->pair_enabled && ctx->max_seg <= v2::MAXSEG && write_e && !e_zero && !xt_for_lut) {
     // a middle layer (reads and writes the edge stream): the CTA-pair kernel
     int r = v2::launch(&ctx->pair, &ctx->tc, l, (float*)ctx->e.p, uvab, (float*)ctx->partials.p, ctx->g, ctx->layers[l],
-                       tvec_edge, ctx->agg_mode, st);
+                       tvec_edge, ctx->agg_mode, st, gn_blocks ? (double*)ctx->gn_part.p : nullptr, gn_blocks);
     if (r) FAIL(ctx, DFB_E_CUDA, "tcgen05 pair edge layer: %s", ctx->tc.err.c_str());
     ctx->launches += ctx->tc.last_launches;
   } else {
@@ -684,6 +754,7 @@ static int run_forward(dfb_ctx* ctx, const float* xt, const float* tvec, bool bi
     }
     e_zero = 1;   // gnn_encoder.py:407: e0 = zeros
   }
+  int gn_fused_blocks = 0;
   for (int l = 0; l < L; ++l) {
     const float* uv = uvab;
     if (l == 0 && !ctx->node_only) {
@@ -694,8 +765,10 @@ static int run_forward(dfb_ctx* ctx, const float* xt, const float* tvec, bool bi
     }
     const float* tv = tvec + (size_t)l * H;
     int write_e = !(ctx->node_only && l == L - 1);
+    // the last layer of the sparse TSP encoder also accumulates the head's GroupNorm statistics (one segment only)
+    const bool want_gn = !ctx->node_only && l == L - 1 && ctx->gn_segments == 1;
     int r = launch_edge_layer(ctx, l, uv, ctx->node_only ? nullptr : tv, write_e, (l == 0) ? e_zero : 0,
-                              (l == 0) ? xt_lut : nullptr, st);
+                              (l == 0) ? xt_lut : nullptr, st, want_gn ? &gn_fused_blocks : nullptr);
     if (r) return r;
     if (ctx->node_only || l < L - 1) {   // TSP never reads h after the last layer (gnn_encoder.py:400)
       k_node_update<<<(V + 7) / 8, 256, 0, st>>>(h, uv, (const float*)ctx->partials.p, g, ctx->layers[l].ln_h_g,
@@ -708,20 +781,35 @@ static int run_forward(dfb_ctx* ctx, const float* xt, const float* tvec, bool bi
   const int R = ctx->node_only ? V : E;
   const int rps = R / ctx->gn_segments;
   const int bps = (rps + GN_ROWS_PER_BLOCK - 1) / GN_ROWS_PER_BLOCK;
-  k_gn_partial<<<dim3(bps, ctx->gn_segments), 256, 0, st>>>(Z, rps, (double*)ctx->gn_part.p);
-  CKL(ctx);
-  k_gn_final<<<dim3(ctx->gn_segments, 32), 256, 0, st>>>((const double*)ctx->gn_part.p, bps, rps, (float*)ctx->gn_stats.p);
-  CKL(ctx);
+  if (gn_fused_blocks > 0) {   // partial sums came out of the last edge layer's epilogue: no extra read of e
+    k_gn_final<<<dim3(1, 32), 256, 0, st>>>((const double*)ctx->gn_part.p, gn_fused_blocks, rps, (float*)ctx->gn_stats.p);
+    CKL(ctx);
+  } else {
+    k_gn_partial<<<dim3(bps, ctx->gn_segments), 256, 0, st>>>(Z, rps, (double*)ctx->gn_part.p);
+    CKL(ctx);
+    k_gn_final<<<dim3(ctx->gn_segments, 32), 256, 0, st>>>((const double*)ctx->gn_part.p, bps, rps, (float*)ctx->gn_stats.p);
+    CKL(ctx);
+  }
   k_head<<<(R + 255) / 256, 256, 0, st>>>(Z, R, rps, (const float*)ctx->gn_stats.p, ctx->node_only ? nullptr : g.perm,
                                       ctx->hp, pa);
   CKL(ctx);
   return DFB_OK;
 }
 
-static int compute_tvecs(dfb_ctx* ctx, const float* tvals_host, int S, cudaStream_t st) {
+// Pinned staging slot for this call: waits (host side) only if the copies of the call that used the slot two calls
+// ago have not executed yet, i.e. the host never runs more than one call ahead of the device.
+static int stage_acquire(dfb_ctx* ctx, int* slot) {
+  *slot = ctx->stage_next;
+  ctx->stage_next = (ctx->stage_next + 1) % dfb_ctx::STAGE_SLOTS;
+  CK(ctx, cudaEventSynchronize(ctx->stage_ev[*slot]));
+  return DFB_OK;
+}
+
+// all time-MLP outputs of the S timesteps staged in h_tvals[slot] -> ctx->tvec [S][L][256]
+static int compute_tvecs(dfb_ctx* ctx, int slot, int S, cudaStream_t st) {
   ENS(ctx, ctx->tvals, std::max<size_t>(4096, (size_t)S) * sizeof(float));
   ENS(ctx, ctx->tvec, (size_t)S * ctx->L * H * sizeof(float));
-  CK(ctx, cudaMemcpyAsync(ctx->tvals.p, tvals_host, (size_t)S * sizeof(float), cudaMemcpyHostToDevice, st));
+  CK(ctx, cudaMemcpyAsync(ctx->tvals.p, ctx->h_tvals[slot], (size_t)S * sizeof(float), cudaMemcpyHostToDevice, st));
   k_time_vectors<<<S, 256, 0, st>>>((const float*)ctx->tvals.p, ctx->tp, (const LayerParams*)ctx->layers_dev.p,
                                     ctx->L, (float*)ctx->tvec.p);
   CKL(ctx);
@@ -733,9 +821,13 @@ extern "C" int dfb_encoder_forward(dfb_ctx* ctx, const float* xt, float t, float
   cudaStream_t st = (cudaStream_t)stream_;
   CK(ctx, cudaSetDevice(ctx->device));
   if (!ctx->graph_ready) FAIL(ctx, DFB_E_INVALID, "dfb_prepare_graph must be called first");
-  int r = compute_tvecs(ctx, &t, 1, st);
+  int slot;
+  int r = stage_acquire(ctx, &slot);
   if (r) return r;
-  CK(ctx, cudaStreamSynchronize(st));   // &t is a stack address
+  ctx->h_tvals[slot][0] = t;
+  r = compute_tvecs(ctx, slot, 1, st);
+  if (r) return r;
+  CK(ctx, cudaEventRecord(ctx->stage_ev[slot], st));
   PosteriorArgs pa{};
   pa.mode = HEAD_FORWARD;
   pa.net_out = out;
@@ -752,7 +844,8 @@ static int step_args(dfb_ctx* ctx, int diffusion_type, const float* consts, int 
   } else {
     FAIL(ctx, DFB_E_INVALID, "Unknown diffusion type %d", diffusion_type);
   }
-  for (int i = 0; i < 4; ++i) pa->c[i] = consts[i];
+  if (consts)
+    for (int i = 0; i < 4; ++i) pa->c[i] = consts[i];
   pa->last = last;
   return DFB_OK;
 }
@@ -767,12 +860,33 @@ extern "C" int dfb_denoise_step(dfb_ctx* ctx, int diffusion_type, const float* x
   PosteriorArgs pa{};
   int r = step_args(ctx, diffusion_type, consts, last, &pa);
   if (r) return r;
-  r = compute_tvecs(ctx, &t, 1, st);
+  int slot;
+  r = stage_acquire(ctx, &slot);
   if (r) return r;
-  CK(ctx, cudaStreamSynchronize(st));
+  ctx->h_tvals[slot][0] = t;
+  r = compute_tvecs(ctx, slot, 1, st);
+  if (r) return r;
+  CK(ctx, cudaEventRecord(ctx->stage_ev[slot], st));
   pa.xt_in = xt_in; pa.uniforms = uniforms; pa.seed = seed; pa.step = (unsigned)step_index;
   pa.xt_out = xt_out; pa.p_out = p_out; pa.net_out = net_out;
   return run_forward(ctx, xt_in, (const float*)ctx->tvec.p, diffusion_type == DFB_DIFFUSION_CATEGORICAL, pa, st);
+}
+
+// the `steps` forwards + posteriors of the loop, every per-step quantity read from device tables
+static int enqueue_loop(dfb_ctx* ctx, int diffusion_type, float* xt, int steps, const float* uniforms, cudaStream_t st) {
+  const size_t N = ctx->node_only ? ctx->g.V : ctx->g.E;
+  for (int i = 0; i < steps; ++i) {
+    PosteriorArgs pa{};
+    int r = step_args(ctx, diffusion_type, nullptr, 0, &pa);
+    if (r) return r;
+    pa.sp = (const StepParams*)ctx->d_steps.p + i;
+    pa.xt_in = xt; pa.xt_out = xt;
+    pa.uniforms = uniforms ? uniforms + (size_t)i * N : nullptr;
+    r = run_forward(ctx, xt, (const float*)ctx->tvec.p + (size_t)i * ctx->L * H,
+                    diffusion_type == DFB_DIFFUSION_CATEGORICAL, pa, st);
+    if (r) return r;
+  }
+  return DFB_OK;
 }
 
 extern "C" int dfb_denoise(dfb_ctx* ctx, int diffusion_type, float* xt, int steps, const int32_t* t1,
@@ -782,24 +896,85 @@ extern "C" int dfb_denoise(dfb_ctx* ctx, int diffusion_type, float* xt, int step
   cudaStream_t st = (cudaStream_t)stream_;
   CK(ctx, cudaSetDevice(ctx->device));
   if (!ctx->graph_ready) FAIL(ctx, DFB_E_INVALID, "dfb_prepare_graph must be called first");
-  if (steps < 1 || steps > 4096) FAIL(ctx, DFB_E_INVALID, "steps %d out of range", steps);
-  std::vector<float> tv(steps);
-  for (int i = 0; i < steps; ++i) tv[i] = (float)t1[i];
-  int r = compute_tvecs(ctx, tv.data(), steps, st);
-  if (r) return r;
-  CK(ctx, cudaStreamSynchronize(st));   // tv is a local; one sync before the loop, none inside
-  const size_t N = ctx->node_only ? ctx->g.V : ctx->g.E;
-  for (int i = 0; i < steps; ++i) {
-    PosteriorArgs pa{};
-    r = step_args(ctx, diffusion_type, consts + 4 * i, last_flags[i], &pa);
-    if (r) return r;
-    pa.xt_in = xt; pa.xt_out = xt;
-    pa.uniforms = uniforms ? uniforms + (size_t)i * N : nullptr;
-    pa.seed = seed; pa.step = (unsigned)i;
-    r = run_forward(ctx, xt, (const float*)ctx->tvec.p + (size_t)i * ctx->L * H,
-                    diffusion_type == DFB_DIFFUSION_CATEGORICAL, pa, st);
+  if (steps < 1 || steps > dfb_ctx::MAX_STEPS) FAIL(ctx, DFB_E_INVALID, "steps %d out of range", steps);
+  if (!ctx->node_only && !ctx->points_ready) FAIL(ctx, DFB_E_INVALID, "dfb_set_points must be called before a TSP forward");
+  {
+    PosteriorArgs chk{};
+    int r = step_args(ctx, diffusion_type, nullptr, 0, &chk);
     if (r) return r;
   }
+  int slot;
+  int r = stage_acquire(ctx, &slot);
+  if (r) return r;
+  for (int i = 0; i < steps; ++i) {
+    ctx->h_tvals[slot][i] = (float)t1[i];
+    StepParams& sp = ctx->h_steps[slot][i];
+    for (int k = 0; k < 4; ++k) sp.c[k] = consts[4 * i + k];
+    sp.last = last_flags[i];
+    sp.step = (unsigned)i;
+    sp.seed = seed;
+  }
+  ENS(ctx, ctx->d_steps, (size_t)dfb_ctx::MAX_STEPS * sizeof(StepParams));
+  r = compute_tvecs(ctx, slot, steps, st);
+  if (r) return r;
+  CK(ctx, cudaMemcpyAsync(ctx->d_steps.p, ctx->h_steps[slot], (size_t)steps * sizeof(StepParams), cudaMemcpyHostToDevice, st));
+  CK(ctx, cudaEventRecord(ctx->stage_ev[slot], st));
+  // the loop state lives in the context's own buffer, so the captured graph does not depend on the caller's pointer
+  const size_t N = ctx->node_only ? ctx->g.V : ctx->g.E;
+  float* x = (float*)ctx->d_xt.p;
+  if (xt != x) CK(ctx, cudaMemcpyAsync(x, xt, N * sizeof(float), cudaMemcpyDeviceToDevice, st));
+
+  const bool want_graph = ctx->capture_enabled && !ctx->capture_broken && !ctx->profiling;
+  if (want_graph) {
+    dfb_ctx::LoopKey key;
+    key.buf_gen = ctx->buf_gen; key.steps = steps; key.diffusion = diffusion_type; key.impl = ctx->edge_impl;
+    key.agg = ctx->agg_mode; key.pair = ctx->pair_enabled; key.uniforms = uniforms;
+    if (!ctx->loop_exec || !(ctx->loop_key == key)) {
+      if (ctx->loop_exec) {
+        cudaGraphExecDestroy(ctx->loop_exec);
+        ctx->loop_exec = nullptr;
+      }
+      const int64_t l0 = ctx->launches;
+      cudaGraph_t graph = nullptr;
+      cudaError_t ce = cudaStreamBeginCapture(ctx->loop_stream, cudaStreamCaptureModeThreadLocal);
+      if (ce == cudaSuccess) {
+        r = enqueue_loop(ctx, diffusion_type, x, steps, uniforms, ctx->loop_stream);
+        ce = cudaStreamEndCapture(ctx->loop_stream, &graph);
+        if (r == DFB_OK && ce == cudaSuccess) ce = cudaGraphInstantiate(&ctx->loop_exec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+      }
+      ctx->loop_launches = ctx->launches - l0;
+      ctx->launches = l0;
+      if (r != DFB_OK || ce != cudaSuccess || !ctx->loop_exec) {
+        // capture is an optimisation: fall back to plain launches (and stop trying) rather than fail the call
+        cudaGetLastError();
+        ctx->loop_exec = nullptr;
+        ctx->capture_broken = true;
+        if (r != DFB_OK) return r;
+      } else {
+        ctx->loop_key = key;
+      }
+    }
+  }
+  if (want_graph && ctx->loop_exec) {
+    CK(ctx, cudaEventRecord(ctx->loop_in, st));
+    CK(ctx, cudaStreamWaitEvent(ctx->loop_stream, ctx->loop_in, 0));
+    CK(ctx, cudaGraphLaunch(ctx->loop_exec, ctx->loop_stream));
+    CK(ctx, cudaEventRecord(ctx->loop_out, ctx->loop_stream));
+    CK(ctx, cudaStreamWaitEvent(st, ctx->loop_out, 0));
+    ctx->launches += ctx->loop_launches;
+  } else {
+    r = enqueue_loop(ctx, diffusion_type, x, steps, uniforms, st);
+    if (r) return r;
+  }
+  if (xt != x) CK(ctx, cudaMemcpyAsync(xt, x, N * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return DFB_OK;
+}
+
+extern "C" int dfb_set_graph_capture(dfb_ctx* ctx, int enabled) {
+  if (!ctx) return DFB_E_INVALID;
+  ctx->capture_enabled = enabled != 0;
+  ctx->capture_broken = false;
   return DFB_OK;
 }
 
@@ -862,7 +1037,7 @@ extern "C" int dfb_debug_edge_gemm(dfb_ctx* ctx, int layer, const float* e_in, f
   if (layer < 0 || layer >= ctx->L) FAIL(ctx, DFB_E_INVALID, "layer out of range");
   ctx->tc.debug_acc = acc_out;
   int r;
-  if (ctx->edge_impl == DFB_EDGE_IMPL_TC && ctx->pair_enabled)
+  if (ctx->edge_impl == DFB_EDGE_IMPL_TC && ctx->pair_enabled && ctx->max_seg <= v2::MAXSEG)
     r = v2::launch(&ctx->pair, &ctx->tc, layer, const_cast<float*>(e_in), (const float*)ctx->uvab.p,
                    (float*)ctx->partials.p, ctx->g, ctx->layers[layer], nullptr, AGG_SUM, st);
   else
@@ -876,13 +1051,13 @@ extern "C" int dfb_debug_edge_gemm(dfb_ctx* ctx, int layer, const float* e_in, f
 }
 
 // Test/tuning hook: read and reset the per-phase cycle counters of the tcgen05 edge kernel
-// (filled only when DFB_TC_PROBE has bit 7 set).  out[8] host.
+// (filled only when DFB_TC_PROBE has bit 7 set, --prof build).  out[32] host.
 extern "C" int dfb_debug_phase_cycles(dfb_ctx* ctx, unsigned long long* out) {
   if (!ctx || !out) return DFB_E_INVALID;
   CK(ctx, cudaSetDevice(ctx->device));
   CK(ctx, cudaDeviceSynchronize());
-  CK(ctx, cudaMemcpy(out, ctx->tc.phase_cycles, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-  CK(ctx, cudaMemset(ctx->tc.phase_cycles, 0, 16 * sizeof(unsigned long long)));
+  CK(ctx, cudaMemcpy(out, ctx->tc.phase_cycles, 32 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  CK(ctx, cudaMemset(ctx->tc.phase_cycles, 0, 32 * sizeof(unsigned long long)));
   return DFB_OK;
 }
 

@@ -992,6 +992,7 @@ struct TcState {
   bool bound = false;
   int last_launches = 0;
   float* zero_row = nullptr;
+  float* zero_row4 = nullptr;   // [4 * 256] zeros: a whole uvab row (pair kernel: gathers of rows past the edge list)
   int* error_flag = nullptr;    // device alias of error_host (host-mapped: readable after a trap)
   int* error_host = nullptr;
   float* debug_acc = nullptr;   // set by the debug entry point for one launch
@@ -1030,8 +1031,10 @@ inline int tc_init(TcState* st, int num_sms) {
   }
   if ((e = cudaMalloc(&st->zero_row, H * sizeof(float))) != cudaSuccess ||
       (e = cudaMemset(st->zero_row, 0, H * sizeof(float))) != cudaSuccess ||
-      (e = cudaMalloc(&st->phase_cycles, 16 * sizeof(unsigned long long))) != cudaSuccess ||
-      (e = cudaMemset(st->phase_cycles, 0, 16 * sizeof(unsigned long long))) != cudaSuccess ||
+      (e = cudaMalloc(&st->zero_row4, 4 * H * sizeof(float))) != cudaSuccess ||
+      (e = cudaMemset(st->zero_row4, 0, 4 * H * sizeof(float))) != cudaSuccess ||
+      (e = cudaMalloc(&st->phase_cycles, 32 * sizeof(unsigned long long))) != cudaSuccess ||
+      (e = cudaMemset(st->phase_cycles, 0, 32 * sizeof(unsigned long long))) != cudaSuccess ||
       (e = cudaHostAlloc(&st->error_host, 4 * sizeof(int), cudaHostAllocMapped)) != cudaSuccess ||
       (e = cudaHostGetDevicePointer((void**)&st->error_flag, st->error_host, 0)) != cudaSuccess) {
     st->err = std::string("tc_init alloc: ") + cudaGetErrorString(e);
@@ -1042,6 +1045,7 @@ inline int tc_init(TcState* st, int num_sms) {
 
 inline void tc_destroy(TcState* st) {
   if (st->zero_row) cudaFree(st->zero_row);
+  if (st->zero_row4) cudaFree(st->zero_row4);
   if (st->error_host) cudaFreeHost(st->error_host);
   if (st->phase_cycles) cudaFree(st->phase_cycles);
   st->zero_row = nullptr;

@@ -31,24 +31,28 @@
 namespace dfb {
 namespace v2 {
 
-constexpr int NA = 3, NB = 3, NOUT = 3;
+constexpr int NA = 5, NB = 4;
 constexpr int STAGE = 16384;                       // one fp32 box [128 rows x 32 cols] == bf16 hi (8 KB) | lo (8 KB)
 constexpr int HALF = 8192;
 constexpr int NWORKW = 16;                         // worker warps
 constexpr int NSERV = 4;                           // service warps
 constexpr int THREADS = (NSERV + NWORKW) * 32;     // 640
 constexpr int NWORK = NWORKW * 32;                 // 512
-constexpr int GBUF = 2048 + 128;                   // gather buffer: [32 rows][8 A | 8 V] fp32 + 4 B-row slots x 32 B
+constexpr int MAXSEG = 8;                          // node segments per 32-edge group the kernel stages B h[row] slots for
+constexpr int GBUF = 2048 + MAXSEG * 32;           // gather buffer: [32 rows][8 A | 8 V] fp32 + B-row slots x 32 B
+constexpr int PART_G = 4 * 2 * GBUF;               // the 8 gather buffers of one part (4 warps): also its E4 staging box
 constexpr int OFF_A = 0;
 constexpr int OFF_B = OFF_A + NA * STAGE;
-constexpr int OFF_OUT = OFF_B + NB * STAGE;
-constexpr int OFF_G = OFF_OUT + NOUT * STAGE;
+constexpr int OFF_G = OFF_B + NB * STAGE;
 constexpr int OFF_PRM = OFF_G + NWORKW * 2 * GBUF;  // ln_e_g, ln_e_b, tau, ln_o_g, ln_o_b, b_O
 constexpr int OFF_IDX = OFF_PRM + 6 * H * 4;        // 2 buffers x { row[128], col[128] }
-constexpr int OFF_BAR = OFF_IDX + 2 * 2 * TC_TILE * 4;
-constexpr int SMEM_BYTES = OFF_BAR + 36 * 8;
+constexpr int IDX_INTS = 2 * TC_TILE + 8;            // row[128] | col[128] | grp_first[4] | grp_pair[4]
+constexpr int OFF_GN = OFF_IDX + 2 * IDX_INTS * 4;   // per worker warp: 8 doubles (4 groups x {sum, sum of squares}) x 2 boxes
+constexpr int OFF_BAR = OFF_GN + NWORKW * 16 * 8;
+constexpr int SMEM_BYTES = OFF_BAR + 48 * 8;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 static_assert(GBUF % 128 == 0, "gather buffers stay 128-byte aligned");
+static_assert(PART_G >= STAGE && PART_G % 1024 == 0 && OFF_G % 1024 == 0, "a part's gather buffers hold one 128B-swizzled fp32 box");
 
 // UMMA instruction descriptor: D=F32, A=B=BF16, K-major, N=256, M=256 (the pair), cute::UMMA::InstrDescriptor
 constexpr uint32_t IDESC2 = (1u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((256u >> 4) << 24);
@@ -61,7 +65,10 @@ struct Params {
   GraphDev g;
   LayerParams lp;
   const float* tvec;      // [256] time vector added on edges (TSP) or nullptr (MIS)
+  const float* zero_row;  // [1024] zeros: gather source of rows past the end of the edge list
   float* debug_acc;       // tests: dump the GEMM1 accumulator [E][256] and stop
+  double* gn_part;        // last layer (sparse TSP head): per-(CTA, lane quarter) GroupNorm(32) partial sums [blocks][32][2], or null
+  int E;                  // number of valid edge rows (GroupNorm statistics skip the padding rows)
   int* error_flag;
   unsigned long long* phase_cycles;
   int agg_mode;
@@ -82,18 +89,21 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// arrive (release at cluster scope) on the LEADER CTA's copy of a barrier, from either CTA of the pair
+// arrive on the LEADER CTA's copy of a barrier, from either CTA of the pair (cutlass umma_arrive_2x1SM_sm0).  No
+// cluster-scope release: ptxas turns that into MEMBAR.ALL.GPU + ERRBAR (8 % of all warp samples in the first version);
+// what is handed over is either TMEM contents (ordered by tcgen05.wait::st + tcgen05.fence::before_thread_sync) or
+// shared memory written for the async proxy (ordered by fence.proxy.async), exactly as in CUTLASS' 2-SM kernels.
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_MASK) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_MASK) : "memory");
 }
-// bounded wait with cluster-scope acquire: pairs with mbar_arrive_leader from the peer CTA
+// bounded wait on a barrier that the peer CTA also arrives on
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity, int* error_flag, int code) {
   const uint32_t addr = smem_u32(bar);
   uint32_t ok = 0;
 #pragma unroll 1
   for (uint32_t spin = 0;; ++spin) {
     asm volatile(
-        "{\n .reg .pred p;\n mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}"
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}"
         : "=r"(ok)
         : "r"(addr), "r"(parity), "r"(20000u)
         : "memory");
@@ -165,27 +175,29 @@ __device__ __forceinline__ uint32_t sw64_off(int r, int j) {
 }
 
 // ----------------------------------------------------------------------------------------------
+// MAXAGG: --aggregation max (gnn_encoder.py:188-191): invalid rows contribute -inf and every segment goes through the
+// general masked reduce; the sum / mean instantiation (the reference default) carries none of that code.
+template <bool MAXAGG>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap emap, const Params P) {
   extern __shared__ __align__(1024) unsigned char smem[];
   float* prm = reinterpret_cast<float*>(smem + OFF_PRM);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-  // box_full: TMA input box landed (local).  TWO barriers per stage (even / odd use of the stage): the converting parts
-  // visit a stage only every other use (part p converts boxes p and p + 4), and a parity wait that is two phases ahead of
-  // the barrier aliases with the phase before - with one barrier per (stage, use parity) a waiter is never more than one
-  // phase ahead.
-  uint64_t* box_full = bars;        // [2 * NA]
-  uint64_t* a_full = bars + 6;      // [NA] LEADER: stage converted by both CTAs (4 warps each)
-  uint64_t* a_empty = bars + 9;     // [NA] MMA commit (multicast): stage consumed
-  uint64_t* b_full = bars + 12;     // [NB] LEADER: both weight halves landed (tx)
-  uint64_t* b_empty = bars + 15;    // [NB] MMA commit (multicast)
-  uint64_t* acc_rdy = bars + 18;    // [2]  MMA commit (multicast): GEMM1 / GEMM2 accumulator complete
-  uint64_t* a2_full = bars + 20;    // [4]  LEADER: GEMM2 A chunk (64 columns of s) written to TMEM by both CTAs
-  uint64_t* res_full = bars + 24;   // [NOUT] residual box landed (local, tx)
-  uint64_t* out_full = bars + 27;   // [NOUT] result box written by the 16 worker warps
-  uint64_t* idx_full = bars + 30;   // [2]  edge endpoints of a tile in shared memory (32 lanes of warp 2)
-  uint64_t* idx_free = bars + 32;   // [2]  the 16 worker warps are done with them
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 34);
+  // Every barrier has waiters that see EVERY one of its phases in order (a parity wait that runs two phases ahead of the
+  // barrier aliases with the phase before): box_full is indexed by the box of the tile, not by the ring stage, because
+  // box b is always converted by the same part (b & 3).
+  uint64_t* box_full = bars;        // [8]  TMA input box b of the tile landed (local, tx)
+  uint64_t* a_full = bars + 8;      // [NA] LEADER: stage converted by both CTAs (4 warps each)
+  uint64_t* a_empty = bars + 13;    // [NA] MMA commit (multicast): stage consumed
+  uint64_t* b_full = bars + 18;     // [NB] LEADER: both weight halves landed (tx)
+  uint64_t* b_empty = bars + 22;    // [NB] MMA commit (multicast)
+  uint64_t* acc_rdy = bars + 26;    // [2]  MMA commit (multicast): GEMM1 / GEMM2 accumulator complete
+  uint64_t* a2_full = bars + 28;    // [4]  LEADER: GEMM2 A chunk (64 columns of s) written to TMEM by both CTAs
+  uint64_t* out_full = bars + 32;   // [4]  part p wrote a result box into its staging (4 warps)
+  uint64_t* stage_free = bars + 36; // [4]  the TMA store has read part p's staging (I/O warp)
+  uint64_t* idx_full = bars + 40;   // [2]  edge endpoints of a tile in shared memory (32 lanes of warp 2)
+  uint64_t* idx_free = bars + 42;   // [2]  the 16 worker warps are done with them
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 44);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -202,11 +214,11 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
       if (P.error_flag) atomicExch(P.error_flag, 99);
       __trap();
     }
-    for (int i = 0; i < NA; ++i) { mbar_init(&box_full[2 * i], 1); mbar_init(&box_full[2 * i + 1], 1); mbar_init(&a_full[i], 8); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < 8; ++i) mbar_init(&box_full[i], 1);
+    for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], 8); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     mbar_init(&acc_rdy[0], 1); mbar_init(&acc_rdy[1], 1);
-    for (int i = 0; i < 4; ++i) mbar_init(&a2_full[i], 2 * NWORKW);
-    for (int i = 0; i < NOUT; ++i) { mbar_init(&res_full[i], 1); mbar_init(&out_full[i], NWORKW); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&a2_full[i], 2 * NWORKW); mbar_init(&out_full[i], 4); mbar_init(&stage_free[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&idx_full[i], 32); mbar_init(&idx_free[i], NWORKW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_proxy_async();
@@ -224,6 +236,7 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
     prm[4 * H + i] = P.lp.ln_o_b[i];
     prm[5 * H + i] = P.lp.b_O[i];
   }
+  for (int i = threadIdx.x; i < NWORKW * 16; i += THREADS) reinterpret_cast<double*>(smem + OFF_GN)[i] = 0.0;
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();   // both CTAs' barriers are initialised before any remote arrive / multicast commit
@@ -274,7 +287,8 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
         }
         umma2_commit(&acc_rdy[0]);
         if (debug) continue;
-        // ---- GEMM2: acc2 = s O^T, A operand (bf16 hi/lo of s) in TMEM: k-step j at columns 16 j (8 hi + 8 lo) ----
+        // ---- GEMM2: acc2 += s O^T on top of the preloaded residual e + b_O; A operand (bf16 hi/lo of s) in TMEM:
+        //      k-step j at columns 16 j (8 hi + 8 lo) ----
         for (int kc = 0; kc < 8; ++kc, ++ub) {
           const uint32_t sb = ub % NB;
           if ((kc & 1) == 0) mbar_wait_cluster(&a2_full[kc >> 1], it & 1, P.error_flag, 13);
@@ -285,7 +299,7 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
           for (int ks = 0; ks < 2; ++ks) {
             const uint32_t ta_hi = tmem_base + (uint32_t)(kc * 32 + ks * 16), ta_lo = ta_hi + 8;
             const uint64_t dbh = umma_desc_sw64(b_hi + ks * 32), dbl = umma_desc_sw64(b_lo + ks * 32);
-            umma2_bf16_ts(tmem_base + 256u, ta_hi, dbh, (kc | ks) ? 1u : 0u);
+            umma2_bf16_ts(tmem_base + 256u, ta_hi, dbh, 1u);
             umma2_bf16_ts(tmem_base + 256u, ta_lo, dbh, 1u);
             umma2_bf16_ts(tmem_base + 256u, ta_hi, dbl, 1u);
           }
@@ -300,14 +314,19 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
     for (int it = 0; it < n_my; ++it) {
       const int tile = tile_of(it), ib = it & 1;
       if (it >= 2) mbar_wait(&idx_free[ib], ((it >> 1) - 1) & 1, P.error_flag, 20);
-      int* s_row = reinterpret_cast<int*>(smem + OFF_IDX) + ib * 2 * TC_TILE;
+      int* s_row = reinterpret_cast<int*>(smem + OFF_IDX) + ib * IDX_INTS;
       int* s_col = s_row + TC_TILE;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int rr = j * 32 + lane, s_edge = tile * TC_TILE + rr;
         const bool ok = tile < P.n_tiles && s_edge < P.g.E;
         s_row[rr] = ok ? __ldg(P.g.row + s_edge) : -1;
-        s_col[rr] = ok ? __ldg(P.g.col + s_edge) : 0;
+        s_col[rr] = ok ? __ldg(P.g.col + s_edge) : -1;
+      }
+      if (lane < 8) {   // (32-edge group, node) pair bookkeeping of the tile's four groups
+        const int grp = tile * 4 + (lane & 3);
+        const int* src = (lane < 4) ? P.g.grp_first : P.g.grp_pair;
+        s_row[2 * TC_TILE + lane] = (grp < P.g.n_groups) ? __ldg(src + grp) : 0;
       }
       mbar_arrive(&idx_full[ib]);
       if (lane == 0) {
@@ -319,29 +338,35 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
         for (int b = 0; b < 8; ++b, ++ga) {
           const uint32_t sa = ga % NA;
           mbar_wait(&a_empty[sa], ((ga / NA) & 1) ^ 1, P.error_flag, 4);
-          uint64_t* bf = &box_full[2 * sa + ((ga / NA) & 1)];
-          mbar_arrive_expect_tx(bf, STAGE);
-          tma_load_2d(smem_base + OFF_A + sa * STAGE, &emap, bf, 32 * b, tile * TC_TILE);
+          mbar_arrive_expect_tx(&box_full[b], STAGE);
+          tma_load_2d(smem_base + OFF_A + sa * STAGE, &emap, &box_full[b], 32 * b, tile * TC_TILE);
         }
       }
       __syncwarp();
     }
   } else if (warp == 3) {
-    // ===================================== E4 I/O: residual boxes in, result boxes out =====================================
+    // ===================================== result boxes out =====================================
+    // part p stages box p, then box p + 4 of a tile in its own gather buffers; the store is issued here and the part is told
+    // when the staging has been read
     if (lane == 0 && !debug) {
-      const int total = n_my * 8;
-      for (int h = 0; h < total + 2; ++h) {
-        if (h >= 2) {
-          const int hs = h - 2, slot = hs % NOUT;
-          mbar_wait(&out_full[slot], (hs / NOUT) & 1, P.error_flag, 8);
-          tma_store_2d(&emap, smem_base + OFF_OUT + slot * STAGE, 32 * (hs & 7), tile_of(hs >> 3) * TC_TILE);
-          tma_store_commit();
-        }
-        if (h < total) {
-          if (h >= NOUT) tma_store_wait_read_n<1>();   // the store that last used this slot (box h-3) has read it
-          const int slot = h % NOUT;
-          mbar_arrive_expect_tx(&res_full[slot], STAGE);
-          tma_load_2d(smem_base + OFF_OUT + slot * STAGE, &emap, &res_full[slot], 32 * (h & 7), tile_of(h >> 3) * TC_TILE);
+      int pending = -1;   // part whose store was issued last and whose staging has not been released yet
+      for (int it = 0; it < n_my; ++it) {
+        for (int j = 0; j < 2; ++j) {
+          for (int p2 = 0; p2 < 4; ++p2) {
+            mbar_wait(&out_full[p2], j, P.error_flag, 8);   // two phases per tile: parity == j
+            tma_store_2d(&emap, smem_base + OFF_G + p2 * PART_G, 32 * (p2 + 4 * j), tile_of(it) * TC_TILE);
+            tma_store_commit();
+            if (pending >= 0) {          // the store before this one has been read once at most one group is pending
+              tma_store_wait_read_n<1>();
+              mbar_arrive(&stage_free[pending]);
+            }
+            pending = p2;
+            if (j == 1 && p2 == 3) {     // last store of the tile: the gathers of the next E1 wait for it
+              tma_store_wait_read_n<0>();
+              mbar_arrive(&stage_free[pending]);
+              pending = -1;
+            }
+          }
         }
       }
       tma_store_wait_all();
@@ -354,9 +379,11 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
     const int r = wq * 32 + lane;            // tile row == TMEM lane
     const int cbase = part * 64;
     unsigned char* gbuf0 = smem + OFF_G + ww * 2 * GBUF;
+    unsigned char* stagebox = smem + OFF_G + part * PART_G;   // this part's E4 staging: [128 rows][32 fp32], 128B swizzle
     const uint32_t t_acc1 = tmem_base + ((uint32_t)(wq * 32) << 16);
     const uint32_t t_acc2 = t_acc1 + 256u;
     auto worker_bar = [] { asm volatile("bar.sync 1, %0;" ::"n"(NWORK) : "memory"); };
+    auto part_bar = [&] { asm volatile("bar.sync %0, 128;" ::"r"(2 + part) : "memory"); };
     auto stat_buf = [&](int p2) { return reinterpret_cast<float*>(smem + OFF_G + (p2 * 4 + wq) * 2 * GBUF); };
 #ifdef DFB_PHASE_PROF
     const bool prof = (P.probe & 128) && ww == 0 && lane == 0;
@@ -366,6 +393,7 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
 #define PHASE(i) do { } while (0)
 #endif
     uint32_t gbox = 0;   // global input-box counter of this CTA (operand ring position)
+    bool prev_valid = false;   // this thread's row of the previous tile is a real edge (GroupNorm statistics)
     for (int it = 0; it <= n_my; ++it) {
       const bool have_tile = it < n_my;      // X phase converts tile `it` and finishes (E4) tile `it - 1`
       const int tile = tile_of(it);
@@ -373,11 +401,148 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
       if (prof) tp = clock64();
 #endif
       worker_bar();   // every warp has left E3 of the previous tile: the gather buffers (LayerNorm exchange) are free
-      int my_row = -1, my_col = 0;
-      uint32_t seg_mask = 0;
-      const float* gptr[4] = {nullptr, nullptr, nullptr, nullptr};
+
+      // ================= X phase: this part's two boxes (part, part + 4): convert tile `it`, finish tile `it - 1` =========
+      for (int j = 0; j < 2; ++j) {
+        const int b = part + 4 * j;
+        float4 xin[8];
+        if (have_tile) {
+          const uint32_t g = gbox + b, sa = g % NA;
+          mbar_wait(&box_full[b], it & 1, P.error_flag, 5);
+          unsigned char* stage = smem + OFF_A + sa * STAGE;
+          uint4 hi[4], lo[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            xin[2 * q] = *reinterpret_cast<const float4*>(stage + sw128_off(r, 2 * q));
+            xin[2 * q + 1] = *reinterpret_cast<const float4*>(stage + sw128_off(r, 2 * q + 1));
+            uint2 h0, l0, h1, l1;
+            split4(xin[2 * q], h0, l0);
+            split4(xin[2 * q + 1], h1, l1);
+            hi[q] = make_uint4(h0.x, h0.y, h1.x, h1.y);
+            lo[q] = make_uint4(l0.x, l0.y, l1.x, l1.y);
+          }
+          // in place: all 128 rows of the box have been read before any bf16 row is written over them
+          part_bar();
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            *reinterpret_cast<uint4*>(stage + sw64_off(r, q)) = hi[q];
+            *reinterpret_cast<uint4*>(stage + HALF + sw64_off(r, q)) = lo[q];
+          }
+          fence_proxy_async();
+          tc_fence_before();   // orders this thread's earlier TMEM accesses (previous tile) before the MMA overwrites acc1
+          __syncwarp();
+          if (lane == 0) mbar_arrive_leader(&a_full[sa]);
+        }
+        if (it > 0 && !debug) {
+          // E4 of the previous tile for box b: acc2 already holds e_in + b_O + s O^T (the residual was preloaded)
+          if (j == 0) {
+            mbar_wait(&acc_rdy[1], (it - 1) & 1, P.error_flag, 7);
+            tc_fence_after();
+          } else {
+            mbar_wait(&stage_free[part], 0, P.error_flag, 10);   // the store of box `part` has read the staging
+          }
+          float gs[8];   // last layer: this row's sums / sums of squares of the 4 GroupNorm groups (8 channels each) of the box
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t v[16];
+            tmem_ld16(t_acc2 + 32 * b + 16 * hh, v);
+            tmem_wait_ld();
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              *reinterpret_cast<float4*>(stagebox + sw128_off(r, 4 * hh + q)) =
+                  make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                              __uint_as_float(v[4 * q + 3]));
+            if (P.gn_part) {
+#pragma unroll
+              for (int g2 = 0; g2 < 2; ++g2) {
+                float sv = 0.f, qv = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float xv = __uint_as_float(v[8 * g2 + i]);
+                  sv += xv;
+                  qv = fmaf(xv, xv, qv);
+                }
+                gs[2 * (2 * hh + g2)] = prev_valid ? sv : 0.f;
+                gs[2 * (2 * hh + g2) + 1] = prev_valid ? qv : 0.f;
+              }
+            }
+          }
+          if (P.gn_part) {
+            // 8 values x 32 rows -> lane k (k < 8) holds the warp total of value k (butterfly transpose-reduce: 9 shuffles),
+            // accumulated in fp64 per warp: the statistics span all E edges of the call (gnn_encoder.py:400, batch dim 1)
+#pragma unroll
+            for (int off = 4; off >= 1; off >>= 1) {
+              const bool up = (lane & off) != 0;
+#pragma unroll
+              for (int i = 0; i < off; ++i) {
+                const float send = up ? gs[i] : gs[i + off], keep = up ? gs[i + off] : gs[i];
+                gs[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+              }
+            }
+            float tot = gs[0];
+            tot += __shfl_xor_sync(0xffffffffu, tot, 8);
+            tot += __shfl_xor_sync(0xffffffffu, tot, 16);
+            // lane L holds the warp total of value index L & 7 (= 2 * group + {sum, sum of squares})
+            if (lane < 8) reinterpret_cast<double*>(smem + OFF_GN)[ww * 16 + j * 8 + lane] += (double)tot;
+          }
+          fence_proxy_async();   // generic-proxy writes -> visible to the TMA store
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&out_full[part]);
+        }
+        if (have_tile && !debug) {
+          // preload GEMM2's accumulator with the residual: acc2[:, box b] = e_in + b_O (this thread's own lane; it read
+          // these columns for E4 just above)
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t v[16];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 bo = *reinterpret_cast<const float4*>(prm + 5 * H + 32 * b + 16 * hh + 4 * q);
+              const float4 xx = xin[4 * hh + q];
+              const float2 o0 = add2(make_float2(xx.x, xx.y), make_float2(bo.x, bo.y));
+              const float2 o1 = add2(make_float2(xx.z, xx.w), make_float2(bo.z, bo.w));
+              v[4 * q] = __float_as_uint(o0.x); v[4 * q + 1] = __float_as_uint(o0.y);
+              v[4 * q + 2] = __float_as_uint(o1.x); v[4 * q + 3] = __float_as_uint(o1.y);
+            }
+            tmem_st16(t_acc2 + 32 * b + 16 * hh, v);
+          }
+        }
+      }
+      gbox += 8;
+      if (!have_tile) break;
+
+      // ---- this tile's edge endpoints, node segments, gather pointers ----
+      const int ib = it & 1;
+      mbar_wait(&idx_full[ib], (it >> 1) & 1, P.error_flag, 21);
+      const int* s_row = reinterpret_cast<const int*>(smem + OFF_IDX) + ib * IDX_INTS;
+      const int* s_col = s_row + TC_TILE;
+      const int my_row = s_row[r];
+      const bool valid = my_row >= 0;
+      uint32_t seg_mask;
+      {
+        int next_row = __shfl_down_sync(0xffffffffu, my_row, 1);
+        bool seg_end = valid && (lane == 31 || next_row != my_row);
+        seg_mask = __ballot_sync(0xffffffffu, seg_end);
+      }
+      const int nseg = __popc(seg_mask);
+      const float* gptr[4];
       const float* bptr = nullptr;
-      int nseg = 0;
+      // A h[col] | V h[col]: lane moves 16-byte unit (lane & 3) of rows (j*8 + lane/4); units 0,1 = A, 2,3 = V.  Rows
+      // past the end of the edge list gather zeros: their messages are exactly 0 (sum / mean) without a select
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int cj = s_col[wq * 32 + j * 8 + (lane >> 2)], uu = lane & 3;
+        gptr[j] = (cj >= 0) ? P.uvab + (size_t)cj * 4 * H + ((uu < 2) ? 2 * H : H) + cbase + (uu & 1) * 4
+                            : P.zero_row + ((uu < 2) ? 2 * H : H) + cbase + (uu & 1) * 4;
+      }
+      // B h[row]: one 32-byte slot per node segment of this warp (the host routes graphs with more than MAXSEG
+      // segments per 32-edge group to the single-CTA kernel)
+      {
+        const int sl = (lane >> 1) & (MAXSEG - 1);
+        const int pos = (int)__fns(seg_mask, 0, sl + 1);
+        const int node = __shfl_sync(0xffffffffu, my_row, (pos >= 0 && pos < 32) ? pos : 0);
+        if (lane < 2 * MAXSEG && sl < nseg) bptr = P.uvab + (size_t)node * 4 * H + 3 * H + cbase + (lane & 1) * 4;
+      }
       const uint32_t goff = (uint32_t)((lane >> 2) * 64 + (((lane & 3) ^ ((lane >> 3) & 3)) << 4));
       auto gather_issue = [&](int step, unsigned char* buf) {
         const uint32_t b32 = smem_u32(buf);
@@ -386,104 +551,14 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
         if (bptr) cp_async16(b32 + 2048 + lane * 16, bptr + step * 8);
         cp_async_commit();
       };
-      if (have_tile) {
-        const int ib = it & 1;
-        mbar_wait(&idx_full[ib], (it >> 1) & 1, P.error_flag, 21);
-        const int* s_row = reinterpret_cast<const int*>(smem + OFF_IDX) + ib * 2 * TC_TILE;
-        const int* s_col = s_row + TC_TILE;
-        my_row = s_row[r];
-        my_col = s_col[r];
-        const bool valid = my_row >= 0;
-        {
-          int next_row = __shfl_down_sync(0xffffffffu, my_row, 1);
-          bool seg_end = valid && (lane == 31 || next_row != my_row);
-          seg_mask = __ballot_sync(0xffffffffu, seg_end);
-        }
-        nseg = __popc(seg_mask);
-        // A h[col] | V h[col]: lane moves 16-byte unit (lane & 3) of rows (j*8 + lane/4); units 0,1 = A, 2,3 = V
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int cj = s_col[wq * 32 + j * 8 + (lane >> 2)], uu = lane & 3;
-          gptr[j] = P.uvab + (size_t)cj * 4 * H + ((uu < 2) ? 2 * H : H) + cbase + (uu & 1) * 4;
-        }
-        // B h[row]: one 32-byte slot per node segment of this warp (up to 4; more -> direct loads in E1)
-        {
-          const int sl = (lane >> 1) & 3;
-          const int pos = (int)__fns(seg_mask, 0, sl + 1);
-          const int node = __shfl_sync(0xffffffffu, my_row, (pos >= 0 && pos < 32) ? pos : 0);
-          if (lane < 8 && sl < nseg && nseg <= 4) bptr = P.uvab + (size_t)node * 4 * H + 3 * H + cbase + (lane & 1) * 4;
-        }
-        if (!debug) {
-          gather_issue(0, gbuf0);
-          gather_issue(1, gbuf0 + GBUF);
-        }
+      if (!debug) {
+        if (it > 0) mbar_wait(&stage_free[part], 1, P.error_flag, 11);   // the store of box part + 4 has read the staging
+        gather_issue(0, gbuf0);
+        gather_issue(1, gbuf0 + GBUF);
       }
-
-      // ================= X phase: convert this tile's boxes (part == box & 3), finish the previous tile (E4) =================
-      for (int b = 0; b < 8; ++b) {
-        // every part observes every phase of the box barriers in order (a parity wait must never run two phases ahead);
-        // the owner of the box (part == b & 3) converts it
-        const uint32_t g = gbox + b, sa = g % NA;
-        if (have_tile) mbar_wait(&box_full[2 * sa + ((g / NA) & 1)], (g / (2 * NA)) & 1, P.error_flag, 5);
-        if (have_tile && (b & 3) == part) {
-          unsigned char* stage = smem + OFF_A + sa * STAGE;
-          uint4 hi[4], lo[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 x0 = *reinterpret_cast<const float4*>(stage + sw128_off(r, 2 * j));
-            const float4 x1 = *reinterpret_cast<const float4*>(stage + sw128_off(r, 2 * j + 1));
-            uint2 h0, l0, h1, l1;
-            split4(x0, h0, l0);
-            split4(x1, h1, l1);
-            hi[j] = make_uint4(h0.x, h0.y, h1.x, h1.y);
-            lo[j] = make_uint4(l0.x, l0.y, l1.x, l1.y);
-          }
-          // in place: all 128 rows of the box have been read before any bf16 row is written over them
-          asm volatile("bar.sync %0, 128;" ::"r"(2 + part) : "memory");
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            *reinterpret_cast<uint4*>(stage + sw64_off(r, j)) = hi[j];
-            *reinterpret_cast<uint4*>(stage + HALF + sw64_off(r, j)) = lo[j];
-          }
-          fence_proxy_async();
-          tc_fence_before();   // orders this thread's earlier TMEM accesses (previous tile) before the MMA overwrites acc1
-          __syncwarp();
-          if (lane == 0) mbar_arrive_leader(&a_full[sa]);
-        }
-        if (it > 0 && !debug) {
-          const uint32_t hh = (uint32_t)(it - 1) * 8 + b, slot = hh % NOUT;
-          if (b == 0) {
-            mbar_wait(&acc_rdy[1], (it - 1) & 1, P.error_flag, 7);
-            tc_fence_after();
-          }
-          mbar_wait(&res_full[slot], (hh / NOUT) & 1, P.error_flag, 10);
-          uint32_t v[8];
-          tmem_ld8(t_acc2 + 32 * b + 8 * part, v);
-          unsigned char* box = smem + OFF_OUT + slot * STAGE;
-          float4* s0 = reinterpret_cast<float4*>(box + sw128_off(r, 2 * part));
-          float4* s1 = reinterpret_cast<float4*>(box + sw128_off(r, 2 * part + 1));
-          const float4 e0 = *s0, e1 = *s1;
-          const float4 bo0 = *reinterpret_cast<const float4*>(prm + 5 * H + 32 * b + 8 * part);
-          const float4 bo1 = *reinterpret_cast<const float4*>(prm + 5 * H + 32 * b + 8 * part + 4);
-          tmem_wait_ld();
-          const float2 o0 = add2(add2(make_float2(e0.x, e0.y), make_float2(__uint_as_float(v[0]), __uint_as_float(v[1]))), make_float2(bo0.x, bo0.y));
-          const float2 o1 = add2(add2(make_float2(e0.z, e0.w), make_float2(__uint_as_float(v[2]), __uint_as_float(v[3]))), make_float2(bo0.z, bo0.w));
-          const float2 o2 = add2(add2(make_float2(e1.x, e1.y), make_float2(__uint_as_float(v[4]), __uint_as_float(v[5]))), make_float2(bo1.x, bo1.y));
-          const float2 o3 = add2(add2(make_float2(e1.z, e1.w), make_float2(__uint_as_float(v[6]), __uint_as_float(v[7]))), make_float2(bo1.z, bo1.w));
-          *s0 = make_float4(o0.x, o0.y, o1.x, o1.y);
-          *s1 = make_float4(o2.x, o2.y, o3.x, o3.y);
-          fence_proxy_async();   // generic-proxy writes -> visible to the TMA store
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&out_full[slot]);
-        }
-      }
-      gbox += 8;
       PHASE(0);   // X phase
-      if (!have_tile) break;
-
-      const bool valid = my_row >= 0;
       const int s_edge = tile * TC_TILE + r;
+      prev_valid = valid;
       mbar_wait(&acc_rdy[0], it & 1, P.error_flag, 6);
       tc_fence_after();
       PHASE(1);   // wait for GEMM1
@@ -508,34 +583,47 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
       }
 
       // ================= E1: e_hat, gate, messages, row statistics (8 steps of 8 columns) =================
-      const int grp = tile * 4 + wq;
-      const int first_node = (grp < P.g.n_groups) ? __ldg(P.g.grp_first + grp) : 0;
-      const size_t pair_base = (grp < P.g.n_groups) ? (size_t)__ldg(P.g.grp_pair + grp) : 0;
-      const int slot_b = min(__popc(seg_mask & ((1u << lane) - 1u)), 3);
-      const float* b_direct = (nseg > 4) ? P.uvab + (size_t)(valid ? my_row : 0) * 4 * H + 3 * H + cbase : nullptr;
-      const uint32_t sw_a = (uint32_t)((lane >> 1) & 3);
+      const int first_node = s_row[2 * TC_TILE + wq];
+      const size_t pair_base = (size_t)s_row[2 * TC_TILE + 4 + wq];
+      const uint32_t gb32 = smem_u32(gbuf0);
+      // shared-memory addresses that are fixed for the tile (buffer 1 = + GBUF)
+      const uint32_t a_row = gb32 + (uint32_t)lane * 64u + ((uint32_t)((lane >> 1) & 3) << 4);   // unit u of my row: a_row ^ (u << 4)
+      // rows past the edge list read the last real segment's slot: every value that enters their (discarded) row stays finite
+      const uint32_t b_slot = gb32 + 2048u + (uint32_t)min(__popc(seg_mask & ((1u << lane) - 1u)), max(min(nseg, MAXSEG), 1) - 1) * 32u;
+      const uint32_t p_st = gb32 + (uint32_t)lane * 4u;                                          // patch[c][lane], pitch 144 B
+      const uint32_t p_ld = gb32 + (uint32_t)(lane & 7) * 144u + (uint32_t)(lane >> 3) * 32u;     // my 8 rows of column lane & 7
+      // Segment structure of this warp's 32 rows.  With at most two node segments (every k-NN / ER workload: a 32-edge
+      // group crosses at most one node boundary when degrees are >= 32) the reduce lane (column lane & 7, rows r_lo..r_lo+7)
+      // needs one number: k0 = how many of its 8 rows belong to the first segment; prefix sums give both segment sums.
+      const int r_lo = (lane >> 3) * 8;
+      const bool fast = !MAXAGG && nseg <= 2 && nseg >= 1;
+      int k0 = 8;
+      float* part0 = nullptr; float* part1 = nullptr;
+      if (fast) {
+        const int e0 = __ffs(seg_mask) - 1;                       // last row of the first segment
+        const int n0 = __shfl_sync(0xffffffffu, my_row, e0);
+        k0 = min(max(e0 + 1 - r_lo, 0), 8);
+        part0 = P.partials + (pair_base + (size_t)(n0 - first_node)) * H + cbase + (lane & 7);
+        if (nseg == 2) {
+          const int n1 = __shfl_sync(0xffffffffu, my_row, 31 - __clz(seg_mask));
+          part1 = P.partials + (pair_base + (size_t)(n1 - first_node)) * H + cbase + (lane & 7);
+        }
+      }
       float2 nK = splat2(0.f), S1p = splat2(0.f), S1q = splat2(0.f), Q1p = splat2(0.f), Q1q = splat2(0.f);
-#pragma unroll 1
-      for (int step = 0; step < 8; ++step) {
-        const int c0 = cbase + step * 8;
-        unsigned char* buf = gbuf0 + (step & 1) * GBUF;
+      auto lds128 = [](uint32_t addr) {
+        float4 v4;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v4.x), "=f"(v4.y), "=f"(v4.z), "=f"(v4.w) : "r"(addr));
+        return v4;
+      };
+      auto sts32 = [](uint32_t addr, float x) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(x) : "memory"); };
+      auto e1_step = [&](const int step, const uint32_t bo) {   // bo = byte offset of this step's buffer (0 or GBUF)
         uint32_t v[8];
-        tmem_ld8(t_acc1 + c0, v);
+        tmem_ld8(t_acc1 + cbase + step * 8, v);
         if (step < 7) cp_async_wait<1>(); else cp_async_wait<0>();
         __syncwarp();                       // this warp's pieces of the step have landed
-        const unsigned char* rowp = buf + lane * 64;
-        const float4 a0 = *reinterpret_cast<const float4*>(rowp + ((0u ^ sw_a) << 4));
-        const float4 a1 = *reinterpret_cast<const float4*>(rowp + ((1u ^ sw_a) << 4));
-        const float4 v0 = *reinterpret_cast<const float4*>(rowp + ((2u ^ sw_a) << 4));
-        const float4 v1 = *reinterpret_cast<const float4*>(rowp + ((3u ^ sw_a) << 4));
-        float4 b0, b1;
-        if (b_direct) {
-          b0 = __ldg(reinterpret_cast<const float4*>(b_direct + step * 8));
-          b1 = __ldg(reinterpret_cast<const float4*>(b_direct + step * 8) + 1);
-        } else {
-          b0 = *reinterpret_cast<const float4*>(buf + 2048 + slot_b * 32);
-          b1 = *reinterpret_cast<const float4*>(buf + 2048 + slot_b * 32 + 16);
-        }
+        const float4 a0 = lds128(a_row + bo), a1 = lds128((a_row ^ 16u) + bo);
+        const float4 v0 = lds128((a_row ^ 32u) + bo), v1 = lds128((a_row ^ 48u) + bo);
+        const float4 b0 = lds128(b_slot + bo), b1 = lds128(b_slot + bo + 16u);
         tmem_wait_ld();
         float2 x[4], m[4];
         x[0] = add2(add2(make_float2(__uint_as_float(v[0]), __uint_as_float(v[1])), make_float2(a0.x, a0.y)), make_float2(b0.x, b0.y));
@@ -556,81 +644,85 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
         m[1] = mul2(sigmoid_mufu2(x[1]), make_float2(v0.z, v0.w));
         m[2] = mul2(sigmoid_mufu2(x[2]), make_float2(v1.x, v1.y));
         m[3] = mul2(sigmoid_mufu2(x[3]), make_float2(v1.z, v1.w));
-        if (!valid) m[0] = m[1] = m[2] = m[3] = splat2((P.agg_mode == AGG_MAX) ? -INFINITY : 0.0f);
+        if (MAXAGG && !valid) m[0] = m[1] = m[2] = m[3] = splat2(-INFINITY);   // sum / mean: the gathered V row is zero
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           v[2 * j] = __float_as_uint(x[j].x);
           v[2 * j + 1] = __float_as_uint(x[j].y);
         }
-        tmem_st8(t_acc1 + c0, v);
+        tmem_st8(t_acc1 + cbase + step * 8, v);
         __syncwarp();                       // every lane has read its A / V / B values: the buffer becomes the patch
-        float* patch = reinterpret_cast<float*>(buf);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {       // transposed [column][row], 36-float pitch: conflict-free
-          patch[(2 * j) * 36 + lane] = m[j].x;
-          patch[(2 * j + 1) * 36 + lane] = m[j].y;
+          sts32(p_st + bo + (uint32_t)(2 * j) * 144u, m[j].x);
+          sts32(p_st + bo + (uint32_t)(2 * j + 1) * 144u, m[j].y);
         }
         __syncwarp();
-        // row-segment reduction: lane = (column = lane % 8, row group = lane / 8) sums its 8 rows of every node segment;
-        // row groups are combined with a fixed shuffle tree; seg_mask is warp-uniform; deterministic, no atomics
-        {
-          const float* pcol = patch + (lane & 7) * 36;
-          const int r_lo = (lane >> 3) * 8, r_hi = r_lo + 7;
-          const float4 t0 = *reinterpret_cast<const float4*>(pcol + r_lo);
-          const float4 t1 = *reinterpret_cast<const float4*>(pcol + r_lo + 4);
+        // row-segment reduction: lane = (column lane & 7, row group lane >> 3); row groups are combined with a fixed
+        // shuffle tree; the segment structure is warp-uniform; deterministic, no atomics
+        const float4 t0 = lds128(p_ld + bo), t1 = lds128(p_ld + bo + 16u);
+        if (fast) {
+          // prefix sums in row order; first segment = the first k0 rows, second = the rest (rows past the edge list are 0)
+          const float p1 = t0.x, p2 = p1 + t0.y, p3 = p2 + t0.z, p4 = p3 + t0.w;
+          const float p5 = p4 + t1.x, p6 = p5 + t1.y, p7 = p6 + t1.z, p8 = p7 + t1.w;
+          const float lo4 = (k0 & 2) ? ((k0 & 1) ? p3 : p2) : ((k0 & 1) ? p1 : 0.0f);
+          const float hi4 = (k0 & 2) ? ((k0 & 1) ? p7 : p6) : ((k0 & 1) ? p5 : p4);
+          float s0 = (k0 & 8) ? p8 : ((k0 & 4) ? hi4 : lo4);
+          float s1 = p8 - s0;
+          s0 += __shfl_xor_sync(0xffffffffu, s0, 8);
+          s1 += __shfl_xor_sync(0xffffffffu, s1, 8);
+          s0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+          s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+          if (lane < 8) {
+            part0[step * 8] = s0;
+            if (part1) part1[step * 8] = s1;
+          }
+        } else {
           const float mv[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
-          if (nseg == 1 && seg_mask == 0x80000000u) {   // the common case: all 32 rows belong to one node
+          const int r_hi = r_lo + 7;
+          uint32_t mask = seg_mask;
+          int start = 0;
+          while (mask) {                         // one iteration per node segment present in this warp
+            const int end = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const int lo = max(start, r_lo) - r_lo, hi = min(end, r_hi) - r_lo;   // my 8 rows of this segment
+            const uint32_t rm = (hi >= lo) ? (((2u << hi) - 1u) & ~((1u << lo) - 1u)) : 0u;
             float run;
-            if (P.agg_mode == AGG_MAX) {
-              run = fmaxf(fmaxf(fmaxf(mv[0], mv[1]), fmaxf(mv[2], mv[3])), fmaxf(fmaxf(mv[4], mv[5]), fmaxf(mv[6], mv[7])));
+            if (MAXAGG) {
+              float q0 = -INFINITY, q1 = -INFINITY;
+#pragma unroll
+              for (int i = 0; i < 8; i += 2) {
+                if ((rm >> i) & 1u) q0 = fmaxf(q0, mv[i]);
+                if ((rm >> (i + 1)) & 1u) q1 = fmaxf(q1, mv[i + 1]);
+              }
+              run = fmaxf(q0, q1);
               run = fmaxf(run, __shfl_xor_sync(0xffffffffu, run, 8));
               run = fmaxf(run, __shfl_xor_sync(0xffffffffu, run, 16));
             } else {
-              run = ((mv[0] + mv[1]) + (mv[2] + mv[3])) + ((mv[4] + mv[5]) + (mv[6] + mv[7]));
+              float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+#pragma unroll
+              for (int i = 0; i < 8; i += 4) {
+                if ((rm >> i) & 1u) q0 += mv[i];
+                if ((rm >> (i + 1)) & 1u) q1 += mv[i + 1];
+                if ((rm >> (i + 2)) & 1u) q2 += mv[i + 2];
+                if ((rm >> (i + 3)) & 1u) q3 += mv[i + 3];
+              }
+              run = (q0 + q1) + (q2 + q3);
               run += __shfl_xor_sync(0xffffffffu, run, 8);
               run += __shfl_xor_sync(0xffffffffu, run, 16);
             }
-            if (lane < 8) P.partials[(pair_base + (size_t)(my_row - first_node)) * H + c0 + lane] = run;
-          } else {
-            uint32_t mask = seg_mask;
-            int start = 0;
-            while (mask) {                         // one iteration per node segment present in this warp
-              const int end = __ffs(mask) - 1;
-              mask &= mask - 1;
-              const int lo = max(start, r_lo) - r_lo, hi = min(end, r_hi) - r_lo;   // my 8 rows of this segment
-              const uint32_t rm = (hi >= lo) ? (((2u << hi) - 1u) & ~((1u << lo) - 1u)) : 0u;
-              float run;
-              if (P.agg_mode == AGG_MAX) {
-                float r0 = -INFINITY, r1 = -INFINITY;
-#pragma unroll
-                for (int i = 0; i < 8; i += 2) {
-                  if ((rm >> i) & 1u) r0 = fmaxf(r0, mv[i]);
-                  if ((rm >> (i + 1)) & 1u) r1 = fmaxf(r1, mv[i + 1]);
-                }
-                run = fmaxf(r0, r1);
-                run = fmaxf(run, __shfl_xor_sync(0xffffffffu, run, 8));
-                run = fmaxf(run, __shfl_xor_sync(0xffffffffu, run, 16));
-              } else {
-                float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
-#pragma unroll
-                for (int i = 0; i < 8; i += 4) {
-                  if ((rm >> i) & 1u) r0 += mv[i];
-                  if ((rm >> (i + 1)) & 1u) r1 += mv[i + 1];
-                  if ((rm >> (i + 2)) & 1u) r2 += mv[i + 2];
-                  if ((rm >> (i + 3)) & 1u) r3 += mv[i + 3];
-                }
-                run = (r0 + r1) + (r2 + r3);
-                run += __shfl_xor_sync(0xffffffffu, run, 8);
-                run += __shfl_xor_sync(0xffffffffu, run, 16);
-              }
-              const int node = __shfl_sync(0xffffffffu, my_row, end);
-              if (lane < 8) P.partials[(pair_base + (size_t)(node - first_node)) * H + c0 + lane] = run;
-              start = end + 1;
-            }
+            const int node = __shfl_sync(0xffffffffu, my_row, end);
+            if (lane < 8) P.partials[(pair_base + (size_t)(node - first_node)) * H + cbase + step * 8 + lane] = run;
+            start = end + 1;
           }
         }
         __syncwarp();                       // patch may be overwritten by the next gather
-        if (step + 2 < 8) gather_issue(step + 2, buf);
+        if (step + 2 < 8) gather_issue(step + 2, gbuf0 + bo);
+      };
+#pragma unroll 1
+      for (int s2 = 0; s2 < 8; s2 += 2) {   // two steps per iteration: the buffer parity is static
+        e1_step(s2, 0u);
+        e1_step(s2 + 1, (uint32_t)GBUF);
       }
       const float K1 = -nK.x, S1 = (S1p.x + S1p.y) + (S1q.x + S1q.y), Q1 = (Q1p.x + Q1p.y) + (Q1q.x + Q1q.y);
       tmem_wait_st();
@@ -753,9 +845,19 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
       }
       PHASE(4);   // E3
     }
+    if (P.gn_part && lane < 8) {
+      // block = (CTA, lane quarter) supplies all 32 groups: warp (part, wq) owns groups 4 (part + 4 j) + g
+      const double* acc = reinterpret_cast<const double*>(smem + OFF_GN) + ww * 16;
+      double* dst = P.gn_part + ((size_t)(blockIdx.x * 4 + wq) * 32) * 2;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int grp_id = 4 * (part + 4 * j) + (lane >> 1);
+        dst[grp_id * 2 + (lane & 1)] = acc[j * 8 + lane];
+      }
+    }
 #ifdef DFB_PHASE_PROF
     if (prof)
-      for (int i = 0; i < 8; ++i) atomicAdd(P.phase_cycles + i, (unsigned long long)pc[i]);
+      for (int i = 0; i < 8; ++i) atomicAdd(P.phase_cycles + 16 + i, (unsigned long long)pc[i]);   // [16..23]: pair kernel
 #endif
 #undef PHASE
   }
@@ -780,7 +882,9 @@ struct State {
 };
 
 inline int init(State* st, TcState* tc) {
-  cudaError_t e = cudaFuncSetAttribute(k_edge_layer_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  cudaError_t e = cudaFuncSetAttribute(k_edge_layer_pair<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(k_edge_layer_pair<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   if (e != cudaSuccess) {
     tc->err = std::string("cudaFuncSetAttribute(pair kernel): ") + cudaGetErrorString(e);
     return -2;
@@ -806,8 +910,11 @@ inline int bind_weights(State* st, TcState* tc, const void* arena, int L) {
 }
 
 // One fused middle layer (reads and writes e): l >= 1 for TSP, any layer with write_e for MIS except layer 0.
+// gn_part != nullptr (last layer of the sparse TSP encoder): the kernel also leaves the head's GroupNorm partial sums,
+// *gn_blocks = number of [32][2] blocks written.
 inline int launch(State* st, TcState* tc, int l, float* e, const float* uvab, float* partials, GraphDev g, LayerParams lp,
-                  const float* tvec_edge, int agg_mode, cudaStream_t stream) {
+                  const float* tvec_edge, int agg_mode, cudaStream_t stream, double* gn_part = nullptr,
+                  int* gn_blocks = nullptr) {
   tc->last_launches = 0;
   if (!st->ready) {
     tc->err = "pair kernel: weights not bound";
@@ -817,18 +924,21 @@ inline int launch(State* st, TcState* tc, int l, float* e, const float* uvab, fl
   if (r) return r;
   Params P;
   P.e = e; P.uvab = uvab; P.partials = partials; P.g = g; P.lp = lp; P.tvec = tvec_edge;
-  P.debug_acc = tc->debug_acc; P.error_flag = tc->error_flag; P.phase_cycles = tc->phase_cycles;
+  P.zero_row = tc->zero_row4; P.debug_acc = tc->debug_acc; P.error_flag = tc->error_flag; P.phase_cycles = tc->phase_cycles;
   P.agg_mode = agg_mode; P.w_row_base = l * 12 * H;
+  P.gn_part = tc->debug_acc ? nullptr : gn_part; P.E = g.E;
   P.n_tiles = (g.E + TC_TILE - 1) / TC_TILE;
   P.probe = tc->probe;
   const int n_pairs = (P.n_tiles + 1) / 2;
   const int clusters = n_pairs < st->max_clusters ? n_pairs : st->max_clusters;
-  k_edge_layer_pair<<<2 * clusters, THREADS, SMEM_BYTES, stream>>>(st->wmap, tc->emap, P);
+  if (agg_mode == AGG_MAX) k_edge_layer_pair<true><<<2 * clusters, THREADS, SMEM_BYTES, stream>>>(st->wmap, tc->emap, P);
+  else k_edge_layer_pair<false><<<2 * clusters, THREADS, SMEM_BYTES, stream>>>(st->wmap, tc->emap, P);
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) {
     tc->err = std::string("pair kernel launch: ") + cudaGetErrorString(err);
     return -2;
   }
+  if (gn_blocks) *gn_blocks = 2 * clusters * 4;
   tc->last_launches = 1;
   return 0;
 }

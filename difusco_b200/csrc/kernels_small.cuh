@@ -267,8 +267,17 @@ struct HeadParams {
   int out_channels;
 };
 enum { HEAD_FORWARD = 0, HEAD_CATEGORICAL = 1, HEAD_GAUSSIAN = 2 };
+// Per-step posterior parameters in DEVICE memory: the captured CUDA graph of the denoise loop reads them through a
+// pointer, so one graph serves every schedule / seed of the same shape (only this small table is re-uploaded).
+struct StepParams {
+  float c[4];
+  int last;
+  unsigned int step;
+  unsigned long long seed;
+};
 struct PosteriorArgs {
   int mode;            // HEAD_*
+  const StepParams* sp;   // when non-null, c / last / seed / step below are taken from *sp
   float c[4];          // categorical c[xt][k] / gaussian {a, b1, b2, noise}
   int last;            // categorical: target_t == 0 -> return clamp(p, min=0)
   const float* xt_in;  // (N,)
@@ -279,7 +288,13 @@ struct PosteriorArgs {
   float* p_out;        // optional
   float* net_out;      // optional (N,out)
 };
-__device__ __forceinline__ void head_posterior(const HeadParams& hp, const PosteriorArgs& pa, size_t o, float l0, float l1) {
+__device__ __forceinline__ void head_posterior(const HeadParams& hp, const PosteriorArgs& pa_in, size_t o, float l0, float l1) {
+  PosteriorArgs pa = pa_in;
+  if (pa.sp) {
+    const StepParams sp = *pa.sp;
+    pa.c[0] = sp.c[0]; pa.c[1] = sp.c[1]; pa.c[2] = sp.c[2]; pa.c[3] = sp.c[3];
+    pa.last = sp.last; pa.step = sp.step; pa.seed = sp.seed;
+  }
   if (pa.net_out) {
     pa.net_out[o * hp.out_channels] = l0;
     if (hp.out_channels == 2) pa.net_out[o * 2 + 1] = l1;

@@ -8,6 +8,13 @@
  * 0 on success or a negative DFB_E_* code; dfb_last_error() gives the message.  Nothing throws
  * across the boundary.  A context is bound to one device and is not thread-safe (one per GPU /
  * per process, as in the reference's one-process-per-GPU DDP launch, train.py:106-115).
+ *
+ * Buffer ownership: every input / output buffer named in a signature is the caller's.  Scratch memory is ONE
+ * arena owned by the context: dfb_load_weights and dfb_prepare_graph size it (device malloc happens only there, and only
+ * when a graph is larger than anything prepared before); dfb_set_points, dfb_encoder_forward, dfb_denoise_step and
+ * dfb_denoise never allocate device or host memory, never synchronise the host with the stream and never read the
+ * environment: per-call scalars travel through two pinned staging slots, per-step tables live in device memory, so
+ * the step path is CUDA-graph capturable - and dfb_denoise itself replays a captured graph.
  */
 #ifndef DIFUSCO_B200_H_
 #define DIFUSCO_B200_H_
@@ -18,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DFB_ABI_VERSION 1
+#define DFB_ABI_VERSION 2
 
 enum {
   DFB_OK = 0,
@@ -108,6 +115,11 @@ int dfb_denoise(dfb_ctx* ctx, int diffusion_type, float* xt, int steps, const in
                 const float* consts, const int32_t* last_flags, const float* uniforms,
                 uint64_t seed, void* stream);
 
+/* dfb_denoise replays the whole loop as ONE captured CUDA graph (on a stream of the library, fenced to `stream` by
+ * events; re-captured only when the prepared graph, the buffers, the implementation switches or `steps` change).
+ * dfb_set_graph_capture(ctx, 0) turns that off (plain launches).  Environment DFB_GRAPH_CAPTURE=0 does the same. */
+int dfb_set_graph_capture(dfb_ctx* ctx, int enabled);
+
 /* End-to-end with HOST buffers (the call bench.py times as `e2e`): H2D of points / edge_index /
  * xt0, graph preparation, `steps` denoise steps, D2H of the final xt into heatmap_out (N,).
  * points may be NULL for MIS. */
@@ -164,7 +176,8 @@ int dfb_profile_end(dfb_ctx* ctx, double* edge_kernel_ms, int64_t* edge_kernel_l
 int dfb_debug_edge_gemm(dfb_ctx* ctx, int layer, const float* e_in, float* acc_out, void* stream);
 
 /* Tuning hook: per-phase cycle counters of the tcgen05 edge kernels (DFB_TC_PROBE bit 7, --prof build); out must hold
- * 16 unsigned 64-bit values (host): [0..7] phases, [8..15] E1 sub-phases of the single-CTA kernel.  Read-and-reset. */
+ * 32 unsigned 64-bit values (host): [0..7] phases and [8..15] E1 sub-phases of the single-CTA kernel, [16..23] phases of
+ * the CTA-pair kernel.  Read-and-reset. */
 int dfb_debug_phase_cycles(dfb_ctx* ctx, unsigned long long* out);
 
 /* Diagnostic: watchdog record of the tcgen05 kernel's bounded barrier waits (host-mapped memory, readable after a

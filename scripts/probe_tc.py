@@ -43,6 +43,11 @@ def t_forward(tag):
     names = ["conv", "waitG1", "E1", "E2", "E3", "waitG2", "E4"]
     print(f"{tag}: cycles/tile " + " ".join(f"{n}={c / ntile_cta:.0f}" for n, c in zip(names, pc)) +
           f" total={sum(pc[:7]) / ntile_cta:.0f}", flush=True)
+    npair = (E + 127) // 128 * 11 * 2          # pair kernel: middle layers only
+    pn = ["X(conv+E4)", "waitG1", "E1", "E2", "E3"]
+    if sum(pc[16:24]):
+      print(f"{tag}: pair kernel cycles/tile " + " ".join(f"{n}={c / npair:.0f}" for n, c in zip(pn, pc[16:21])) +
+            f" total={sum(pc[16:24]) / npair:.0f}", flush=True)
     sub = ["tmemwait", "gatherwait", "math", "gissue", "reduce"]
     print(f"{tag}: E1 sub-phases cycles/tile " + " ".join(f"{n}={c / ntile_cta:.0f}" for n, c in zip(sub, pc[8:13])), flush=True)
 

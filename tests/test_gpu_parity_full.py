@@ -105,14 +105,15 @@ def _fused_vs_golden(model, task, g, useed, diffusion):
   got = x.cpu().numpy()
   ref = g["xt_out"][-1].reshape(-1)
   if diffusion == "categorical":
-    # a sample can only differ from the reference's where |p - u| is inside fp32 noise; such a flip legitimately changes
-    # everything downstream, so the comparison of the free-running loop is only meaningful without near-ties
-    near = [np.abs(g["p"][i].reshape(-1) - u[i]) < 10 * TOL for i in range(steps - 1)]
-    if any(nm.any() for nm in near):
-      pytest.skip("golden trajectory has a near-tie |p - u| < 1e-3: free-running comparison undefined")
-    assert np.abs(got - ref).max() < TOL * max(ref.max(), 1e-3)
     big = ref > 1e-3
-    assert np.abs(got[big] / ref[big] - 1).max() < TOL
+    ok = np.abs(got - ref).max() < TOL * max(ref.max(), 1e-3) and np.abs(got[big] / ref[big] - 1).max() < TOL
+    if not ok:
+      # a sample can only differ from the reference's where |p - u| is inside the 1e-4 contract on p; such a flip
+      # legitimately changes everything downstream, so a mismatch is excused ONLY when the golden trajectory has such a tie
+      near = [np.abs(g["p"][i].reshape(-1) - u[i]) < TOL for i in range(steps - 1)]
+      if any(nm.any() for nm in near):
+        pytest.skip("golden trajectory has a tie |p - u| < 1e-4 and the free-running loop took the other branch")
+    assert ok
   else:
     assert rel_linf(got, ref) < TOL
 
@@ -146,9 +147,6 @@ def test_fused_loop_tsp500_vs_oracle_free_running(weights2):
   rec = []
   ref = orc.denoise(orc.Weights(weights2), "tsp", "categorical", ei, xt0, points=pts, steps=steps, uniforms=us,
                     record=rec).numpy()
-  for i, r in enumerate(rec[:-1]):
-    if (np.abs(r["p"].numpy() - us[i]) < 10 * TOL).any():
-      pytest.skip(f"near-tie at step {i}")
   m = G.tsp_model(weights2, "tc", sparse_factor=50, inference_diffusion_steps=steps)
   m._prepare(G.cu(pts), G.cu(ei), torch.device("cuda"))
   sched = orc.inference_schedule("cosine", 1000, steps)
@@ -160,7 +158,12 @@ def test_fused_loop_tsp500_vs_oracle_free_running(weights2):
   m.model.engine().denoise(_cabi.CATEGORICAL, x.data_ptr(), t1s, cs, ls, G.cu(np.stack(us)).data_ptr(), 0,
                            torch.cuda.current_stream().cuda_stream)
   got = x.cpu().numpy()
-  assert np.abs(got - ref).max() < TOL * max(ref.max(), 1e-3)
+  ok = np.abs(got - ref).max() < TOL * max(ref.max(), 1e-3)
+  if not ok:
+    for i, r in enumerate(rec[:-1]):
+      if (np.abs(r["p"].numpy() - us[i]) < TOL).any():
+        pytest.skip(f"tie |p - u| < 1e-4 at step {i}: the trajectories may legitimately part there")
+  assert ok
 
 
 # ------------------------------------------------------------------------------------------------
@@ -226,3 +229,28 @@ def test_forward_tsp_single_cta_kernel_vs_pair_kernel(weights2):
   a = G.encoder(weights2, 2, impl="tc")(G.cu(pts), torch.tensor([555.0]), G.cu(xt), G.cu(ei)).cpu().numpy()
   b = G.encoder(weights2, 2, impl="tc1")(G.cu(pts), torch.tensor([555.0]), G.cu(xt), G.cu(ei)).cpu().numpy()
   assert rel_linf(a, b) < 2e-5
+
+
+# ------------------------------------------------------------------------------------------------
+# the captured CUDA graph of the loop == plain launches, across seeds / schedules / re-captures
+# ------------------------------------------------------------------------------------------------
+def test_fused_loop_graph_capture_matches_plain_launches(weights2):
+  m = G.tsp_model(weights2, "tc", sparse_factor=10, inference_diffusion_steps=8)
+  pts, ei = syn.tsp_sparse_batch(80, 10, 2, seed=12)
+  xt0 = (syn.initial_noise(ei.shape[1], 4) > 0).astype(np.float32)
+  ctx = m.model.engine()
+  ctx.set_graph_capture(True)
+  a1 = m.denoise_heatmap(G.cu(pts), G.cu(ei), G.cu(xt0), seed=5).cpu().numpy()    # captures
+  b1 = m.denoise_heatmap(G.cu(pts), G.cu(ei), G.cu(xt0), seed=6).cpu().numpy()    # replays with another seed
+  a2 = m.denoise_heatmap(G.cu(pts), G.cu(ei), G.cu(xt0), seed=5).cpu().numpy()    # replays
+  ctx.set_graph_capture(False)
+  a3 = m.denoise_heatmap(G.cu(pts), G.cu(ei), G.cu(xt0), seed=5).cpu().numpy()    # plain launches
+  b3 = m.denoise_heatmap(G.cu(pts), G.cu(ei), G.cu(xt0), seed=6).cpu().numpy()
+  ctx.set_graph_capture(True)
+  assert np.array_equal(a1, a2) and np.array_equal(a1, a3) and np.array_equal(b1, b3) and not np.array_equal(a1, b1)
+  # another graph shape -> re-capture; back to the first shape -> re-capture again, same answer
+  pts2, ei2 = syn.tsp_sparse_batch(60, 10, 3, seed=13)
+  x2 = (syn.initial_noise(ei2.shape[1], 5) > 0).astype(np.float32)
+  c1 = m.denoise_heatmap(G.cu(pts2), G.cu(ei2), G.cu(x2), seed=9).cpu().numpy()
+  a4 = m.denoise_heatmap(G.cu(pts), G.cu(ei), G.cu(xt0), seed=5).cpu().numpy()
+  assert np.array_equal(a1, a4) and np.isfinite(c1).all()

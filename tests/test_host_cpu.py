@@ -35,7 +35,7 @@ def test_library_builds_and_exports_every_declared_symbol():
   for name in declared:
     assert hasattr(L, name), f"{name} declared in include/difusco_b200.h but not exported"
   assert sorted(_cabi.SYMBOLS) == declared
-  assert L.dfb_abi_version() == 1
+  assert L.dfb_abi_version() == 2
 
 
 def test_no_cpu_fallback_context_fails_loudly():
