@@ -48,7 +48,8 @@ constexpr int OFF_PRM = OFF_G + NWORKW * 2 * GBUF;  // ln_e_g, ln_e_b, tau, ln_o
 constexpr int OFF_IDX = OFF_PRM + 6 * H * 4;        // 2 buffers x { row[128], col[128] }
 constexpr int IDX_INTS = 2 * TC_TILE + 8;            // row[128] | col[128] | grp_first[4] | grp_pair[4]
 constexpr int OFF_GN = OFF_IDX + 2 * IDX_INTS * 4;   // per worker warp: 8 doubles (4 groups x {sum, sum of squares}) x 2 boxes
-constexpr int OFF_BAR = OFF_GN + NWORKW * 16 * 8;
+constexpr int OFF_SEG = OFF_GN + NWORKW * 16 * 8;      // per worker warp: node of each of its (<= MAXSEG) segments
+constexpr int OFF_BAR = OFF_SEG + NWORKW * MAXSEG * 4;
 constexpr int SMEM_BYTES = OFF_BAR + 48 * 8;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 static_assert(GBUF % 128 == 0, "gather buffers stay 128-byte aligned");
@@ -177,7 +178,9 @@ __device__ __forceinline__ uint32_t sw64_off(int r, int j) {
 // ----------------------------------------------------------------------------------------------
 // MAXAGG: --aggregation max (gnn_encoder.py:188-191): invalid rows contribute -inf and every segment goes through the
 // general masked reduce; the sum / mean instantiation (the reference default) carries none of that code.
-template <bool MAXAGG>
+// GNSTATS: the last layer of the sparse TSP encoder also leaves the head's GroupNorm partial sums (own instantiation: the
+// extra live values would otherwise cost the other eleven layers registers in the X phase).
+template <bool MAXAGG, bool GNSTATS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap emap, const Params P) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -265,12 +268,24 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
     // ===================================== MMA issue (leader CTA only) =====================================
     if (leader && lane == 0) {
       uint32_t ub = 0, ga = 0;
+#ifdef DFB_PHASE_PROF
+      long long wa = 0, wb = 0, w2 = 0, tq;
+#define MMA_T0() do { tq = clock64(); } while (0)
+#define MMA_T1(acc) do { acc += clock64() - tq; } while (0)
+#else
+#define MMA_T0() do { } while (0)
+#define MMA_T1(acc) do { } while (0)
+#endif
       for (int it = 0; it < n_my; ++it) {
         // ---- GEMM1: acc1 = e C^T, 8 K-chunks of 32, A and B from shared memory ----
         for (int kc = 0; kc < 8; ++kc, ++ub, ++ga) {
           const uint32_t sb = ub % NB, sa = ga % NA;
+          MMA_T0();
           mbar_wait(&b_full[sb], (ub / NB) & 1, P.error_flag, 2);
+          MMA_T1(wb);
+          MMA_T0();
           mbar_wait_cluster(&a_full[sa], (ga / NA) & 1, P.error_flag, 3);
+          MMA_T1(wa);
           tc_fence_after();
           const uint32_t a_hi = smem_base + OFF_A + sa * STAGE, a_lo = a_hi + HALF;
           const uint32_t b_hi = smem_base + OFF_B + sb * STAGE, b_lo = b_hi + HALF;
@@ -291,8 +306,12 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
         //      k-step j at columns 16 j (8 hi + 8 lo) ----
         for (int kc = 0; kc < 8; ++kc, ++ub) {
           const uint32_t sb = ub % NB;
+          MMA_T0();
           if ((kc & 1) == 0) mbar_wait_cluster(&a2_full[kc >> 1], it & 1, P.error_flag, 13);
+          MMA_T1(w2);
+          MMA_T0();
           mbar_wait(&b_full[sb], (ub / NB) & 1, P.error_flag, 12);
+          MMA_T1(wb);
           tc_fence_after();
           const uint32_t b_hi = smem_base + OFF_B + sb * STAGE, b_lo = b_hi + HALF;
 #pragma unroll
@@ -307,6 +326,15 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
         }
         umma2_commit(&acc_rdy[1]);
       }
+#ifdef DFB_PHASE_PROF
+      if (P.probe & 128) {   // MMA thread's waits: [21] A stages (GEMM1), [22] weights, [23] GEMM2 A chunks; per tile PAIR
+        atomicAdd(P.phase_cycles + 21, (unsigned long long)wa);
+        atomicAdd(P.phase_cycles + 22, (unsigned long long)wb);
+        atomicAdd(P.phase_cycles + 23, (unsigned long long)w2);
+      }
+#endif
+#undef MMA_T0
+#undef MMA_T1
     }
   } else if (warp == 2) {
     // ===================================== edge endpoints + input boxes =====================================
@@ -387,10 +415,12 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
     auto stat_buf = [&](int p2) { return reinterpret_cast<float*>(smem + OFF_G + (p2 * 4 + wq) * 2 * GBUF); };
 #ifdef DFB_PHASE_PROF
     const bool prof = (P.probe & 128) && ww == 0 && lane == 0;
-    long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tp = 0;
+    long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tp = 0, px[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tx = 0;
 #define PHASE(i) do { if (prof) { long long _n = clock64(); pc[i] += _n - tp; tp = _n; } } while (0)
+#define XSUB(i) do { if (prof) { long long _n = clock64(); px[i] += _n - tx; tx = _n; } } while (0)
 #else
 #define PHASE(i) do { } while (0)
+#define XSUB(i) do { } while (0)
 #endif
     uint32_t gbox = 0;   // global input-box counter of this CTA (operand ring position)
     bool prev_valid = false;   // this thread's row of the previous tile is a real edge (GroupNorm statistics)
@@ -403,35 +433,35 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
       worker_bar();   // every warp has left E3 of the previous tile: the gather buffers (LayerNorm exchange) are free
 
       // ================= X phase: this part's two boxes (part, part + 4): convert tile `it`, finish tile `it - 1` =========
+#ifdef DFB_PHASE_PROF
+      if (prof) tx = clock64();
+#endif
       for (int j = 0; j < 2; ++j) {
         const int b = part + 4 * j;
         float4 xin[8];
         if (have_tile) {
           const uint32_t g = gbox + b, sa = g % NA;
           mbar_wait(&box_full[b], it & 1, P.error_flag, 5);
+          XSUB(0);   // wait for the input box
           unsigned char* stage = smem + OFF_A + sa * STAGE;
-          uint4 hi[4], lo[4];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            xin[2 * q] = *reinterpret_cast<const float4*>(stage + sw128_off(r, 2 * q));
-            xin[2 * q + 1] = *reinterpret_cast<const float4*>(stage + sw128_off(r, 2 * q + 1));
-            uint2 h0, l0, h1, l1;
-            split4(xin[2 * q], h0, l0);
-            split4(xin[2 * q + 1], h1, l1);
-            hi[q] = make_uint4(h0.x, h0.y, h1.x, h1.y);
-            lo[q] = make_uint4(l0.x, l0.y, l1.x, l1.y);
-          }
-          // in place: all 128 rows of the box have been read before any bf16 row is written over them
+          for (int q = 0; q < 8; ++q) xin[q] = *reinterpret_cast<const float4*>(stage + sw128_off(r, q));
+          // in place: all 128 rows of the box have been read before any bf16 row is written over them (only the fp32
+          // values stay live across the barrier; they are also the residual preloaded below)
           part_bar();
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            *reinterpret_cast<uint4*>(stage + sw64_off(r, q)) = hi[q];
-            *reinterpret_cast<uint4*>(stage + HALF + sw64_off(r, q)) = lo[q];
+            uint2 h0, l0, h1, l1;
+            split4(xin[2 * q], h0, l0);
+            split4(xin[2 * q + 1], h1, l1);
+            *reinterpret_cast<uint4*>(stage + sw64_off(r, q)) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+            *reinterpret_cast<uint4*>(stage + HALF + sw64_off(r, q)) = make_uint4(l0.x, l0.y, l1.x, l1.y);
           }
           fence_proxy_async();
           tc_fence_before();   // orders this thread's earlier TMEM accesses (previous tile) before the MMA overwrites acc1
           __syncwarp();
           if (lane == 0) mbar_arrive_leader(&a_full[sa]);
+          XSUB(1);   // conversion
         }
         if (it > 0 && !debug) {
           // E4 of the previous tile for box b: acc2 already holds e_in + b_O + s O^T (the residual was preloaded)
@@ -441,33 +471,30 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
           } else {
             mbar_wait(&stage_free[part], 0, P.error_flag, 10);   // the store of box `part` has read the staging
           }
+          XSUB(2);   // wait for GEMM2 / the staging
           float gs[8];   // last layer: this row's sums / sums of squares of the 4 GroupNorm groups (8 channels each) of the box
 #pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            uint32_t v[16];
-            tmem_ld16(t_acc2 + 32 * b + 16 * hh, v);
+          for (int g2 = 0; g2 < 4; ++g2) {   // 8 columns == one GroupNorm group at a time: few live registers next to xin
+            uint32_t v[8];
+            tmem_ld8(t_acc2 + 32 * b + 8 * g2, v);
             tmem_wait_ld();
+            *reinterpret_cast<float4*>(stagebox + sw128_off(r, 2 * g2)) =
+                make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
+            *reinterpret_cast<float4*>(stagebox + sw128_off(r, 2 * g2 + 1)) =
+                make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7]));
+            if (GNSTATS) {
+              float sv = 0.f, qv = 0.f;
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-              *reinterpret_cast<float4*>(stagebox + sw128_off(r, 4 * hh + q)) =
-                  make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
-                              __uint_as_float(v[4 * q + 3]));
-            if (P.gn_part) {
-#pragma unroll
-              for (int g2 = 0; g2 < 2; ++g2) {
-                float sv = 0.f, qv = 0.f;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  const float xv = __uint_as_float(v[8 * g2 + i]);
-                  sv += xv;
-                  qv = fmaf(xv, xv, qv);
-                }
-                gs[2 * (2 * hh + g2)] = prev_valid ? sv : 0.f;
-                gs[2 * (2 * hh + g2) + 1] = prev_valid ? qv : 0.f;
+              for (int i = 0; i < 8; ++i) {
+                const float xv = __uint_as_float(v[i]);
+                sv += xv;
+                qv = fmaf(xv, xv, qv);
               }
+              gs[2 * g2] = prev_valid ? sv : 0.f;
+              gs[2 * g2 + 1] = prev_valid ? qv : 0.f;
             }
           }
-          if (P.gn_part) {
+          if (GNSTATS) {
             // 8 values x 32 rows -> lane k (k < 8) holds the warp total of value k (butterfly transpose-reduce: 9 shuffles),
             // accumulated in fp64 per warp: the statistics span all E edges of the call (gnn_encoder.py:400, batch dim 1)
 #pragma unroll
@@ -488,6 +515,7 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
           fence_proxy_async();   // generic-proxy writes -> visible to the TMA store
           __syncwarp();
           if (lane == 0) mbar_arrive(&out_full[part]);
+          XSUB(3);   // E4 copy-out
         }
         if (have_tile && !debug) {
           // preload GEMM2's accumulator with the residual: acc2[:, box b] = e_in + b_O (this thread's own lane; it read
@@ -506,6 +534,7 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
             }
             tmem_st16(t_acc2 + 32 * b + 16 * hh, v);
           }
+          XSUB(4);   // residual preload
         }
       }
       gbox += 8;
@@ -538,21 +567,28 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
       // B h[row]: one 32-byte slot per node segment of this warp (the host routes graphs with more than MAXSEG
       // segments per 32-edge group to the single-CTA kernel)
       {
+        int* segrow = reinterpret_cast<int*>(smem + OFF_SEG) + ww * MAXSEG;
+        const int my_seg = __popc(seg_mask & ((1u << lane) - 1u));
+        if (((seg_mask >> lane) & 1u) && my_seg < MAXSEG) segrow[my_seg] = my_row;   // the last row of a segment publishes its node
+        __syncwarp();
         const int sl = (lane >> 1) & (MAXSEG - 1);
-        const int pos = (int)__fns(seg_mask, 0, sl + 1);
-        const int node = __shfl_sync(0xffffffffu, my_row, (pos >= 0 && pos < 32) ? pos : 0);
-        if (lane < 2 * MAXSEG && sl < nseg) bptr = P.uvab + (size_t)node * 4 * H + 3 * H + cbase + (lane & 1) * 4;
+        if (lane < 2 * MAXSEG && sl < nseg) bptr = P.uvab + (size_t)segrow[sl] * 4 * H + 3 * H + cbase + (lane & 1) * 4;
       }
       const uint32_t goff = (uint32_t)((lane >> 2) * 64 + (((lane & 3) ^ ((lane >> 3) & 3)) << 4));
       auto gather_issue = [&](int step, unsigned char* buf) {
+#ifdef DFB_PHASE_PROF
+        if (P.probe & 1) { cp_async_commit(); return; }   // tuning build: E1 without its gather traffic (results wrong)
+#endif
         const uint32_t b32 = smem_u32(buf);
 #pragma unroll
         for (int j = 0; j < 4; ++j) cp_async16(b32 + j * 512 + goff, gptr[j] + step * 8);
         if (bptr) cp_async16(b32 + 2048 + lane * 16, bptr + step * 8);
         cp_async_commit();
       };
+      XSUB(5);   // endpoints, segments, gather pointers
       if (!debug) {
         if (it > 0) mbar_wait(&stage_free[part], 1, P.error_flag, 11);   // the store of box part + 4 has read the staging
+        XSUB(6);   // wait for the staging before the first gathers
         gather_issue(0, gbuf0);
         gather_issue(1, gbuf0 + GBUF);
       }
@@ -640,10 +676,18 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
           Q1p = fma2(d2, d2, Q1p);
           Q1q = fma2(d3, d3, Q1q);
         }
-        m[0] = mul2(sigmoid_mufu2(x[0]), make_float2(v0.x, v0.y));
-        m[1] = mul2(sigmoid_mufu2(x[1]), make_float2(v0.z, v0.w));
-        m[2] = mul2(sigmoid_mufu2(x[2]), make_float2(v1.x, v1.y));
-        m[3] = mul2(sigmoid_mufu2(x[3]), make_float2(v1.z, v1.w));
+#ifdef DFB_PHASE_PROF
+        if (P.probe & 2) {   // tuning build: E1 without the sigmoid (results wrong)
+          m[0] = mul2(x[0], make_float2(v0.x, v0.y)); m[1] = mul2(x[1], make_float2(v0.z, v0.w));
+          m[2] = mul2(x[2], make_float2(v1.x, v1.y)); m[3] = mul2(x[3], make_float2(v1.z, v1.w));
+        } else
+#endif
+        {
+          m[0] = mul2(sigmoid_mufu2(x[0]), make_float2(v0.x, v0.y));
+          m[1] = mul2(sigmoid_mufu2(x[1]), make_float2(v0.z, v0.w));
+          m[2] = mul2(sigmoid_mufu2(x[2]), make_float2(v1.x, v1.y));
+          m[3] = mul2(sigmoid_mufu2(x[3]), make_float2(v1.z, v1.w));
+        }
         if (MAXAGG && !valid) m[0] = m[1] = m[2] = m[3] = splat2(-INFINITY);   // sum / mean: the gathered V row is zero
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -845,7 +889,7 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
       }
       PHASE(4);   // E3
     }
-    if (P.gn_part && lane < 8) {
+    if (GNSTATS && lane < 8) {
       // block = (CTA, lane quarter) supplies all 32 groups: warp (part, wq) owns groups 4 (part + 4 j) + g
       const double* acc = reinterpret_cast<const double*>(smem + OFF_GN) + ww * 16;
       double* dst = P.gn_part + ((size_t)(blockIdx.x * 4 + wq) * 32) * 2;
@@ -856,10 +900,13 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
       }
     }
 #ifdef DFB_PHASE_PROF
-    if (prof)
-      for (int i = 0; i < 8; ++i) atomicAdd(P.phase_cycles + 16 + i, (unsigned long long)pc[i]);   // [16..23]: pair kernel
+    if (prof) {
+      for (int i = 0; i < 5; ++i) atomicAdd(P.phase_cycles + 16 + i, (unsigned long long)pc[i]);   // [16..20]: pair kernel phases
+      for (int i = 0; i < 8; ++i) atomicAdd(P.phase_cycles + 24 + i, (unsigned long long)px[i]);   // [24..31]: X sub-phases
+    }
 #endif
 #undef PHASE
+#undef XSUB
   }
 
   // teardown: nobody may leave while the peer can still signal this CTA's barriers or read its shared memory
@@ -882,9 +929,13 @@ struct State {
 };
 
 inline int init(State* st, TcState* tc) {
-  cudaError_t e = cudaFuncSetAttribute(k_edge_layer_pair<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  cudaError_t e = cudaFuncSetAttribute(k_edge_layer_pair<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(k_edge_layer_pair<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    e = cudaFuncSetAttribute(k_edge_layer_pair<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(k_edge_layer_pair<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(k_edge_layer_pair<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   if (e != cudaSuccess) {
     tc->err = std::string("cudaFuncSetAttribute(pair kernel): ") + cudaGetErrorString(e);
     return -2;
@@ -931,8 +982,11 @@ inline int launch(State* st, TcState* tc, int l, float* e, const float* uvab, fl
   P.probe = tc->probe;
   const int n_pairs = (P.n_tiles + 1) / 2;
   const int clusters = n_pairs < st->max_clusters ? n_pairs : st->max_clusters;
-  if (agg_mode == AGG_MAX) k_edge_layer_pair<true><<<2 * clusters, THREADS, SMEM_BYTES, stream>>>(st->wmap, tc->emap, P);
-  else k_edge_layer_pair<false><<<2 * clusters, THREADS, SMEM_BYTES, stream>>>(st->wmap, tc->emap, P);
+  const bool gn = P.gn_part != nullptr;
+  if (agg_mode == AGG_MAX && gn) k_edge_layer_pair<true, true><<<2 * clusters, THREADS, SMEM_BYTES, stream>>>(st->wmap, tc->emap, P);
+  else if (agg_mode == AGG_MAX) k_edge_layer_pair<true, false><<<2 * clusters, THREADS, SMEM_BYTES, stream>>>(st->wmap, tc->emap, P);
+  else if (gn) k_edge_layer_pair<false, true><<<2 * clusters, THREADS, SMEM_BYTES, stream>>>(st->wmap, tc->emap, P);
+  else k_edge_layer_pair<false, false><<<2 * clusters, THREADS, SMEM_BYTES, stream>>>(st->wmap, tc->emap, P);
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) {
     tc->err = std::string("pair kernel launch: ") + cudaGetErrorString(err);

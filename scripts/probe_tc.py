@@ -47,7 +47,12 @@ def t_forward(tag):
     pn = ["X(conv+E4)", "waitG1", "E1", "E2", "E3"]
     if sum(pc[16:24]):
       print(f"{tag}: pair kernel cycles/tile " + " ".join(f"{n}={c / npair:.0f}" for n, c in zip(pn, pc[16:21])) +
-            f" total={sum(pc[16:24]) / npair:.0f}", flush=True)
+            f" total={sum(pc[16:21]) / npair:.0f}", flush=True)
+      xn = ["boxwait", "conv", "waitG2/stage", "E4copy", "preload", "setup", "stagewait"]
+      print(f"{tag}: pair kernel X sub-phases cycles/tile " + " ".join(f"{n}={c / npair:.0f}" for n, c in zip(xn, pc[24:31])), flush=True)
+      nlead = npair / 2   # tile pairs: the leader CTA's MMA thread
+      print(f"{tag}: pair kernel MMA-thread waits per tile pair: A stages {pc[21] / nlead:.0f}  weights {pc[22] / nlead:.0f}  "
+            f"GEMM2 A chunks {pc[23] / nlead:.0f}", flush=True)
     sub = ["tmemwait", "gatherwait", "math", "gissue", "reduce"]
     print(f"{tag}: E1 sub-phases cycles/tile " + " ".join(f"{n}={c / ntile_cta:.0f}" for n, c in zip(sub, pc[8:13])), flush=True)
 
