@@ -98,10 +98,12 @@ def measured_peaks():
 
 
 def ncu_traffic():
-  p = os.path.join(ROOT, "profiles", "edge_kernel_traffic.json")
+  """dram__bytes_read.sum + dram__bytes_write.sum of ALL launches of one denoise step of the headline workload, from the
+  committed ncu pass (profiles/r02_step_traffic.json; same scope as roofline.achieved: the whole step)."""
+  p = os.path.join(ROOT, "profiles", "r02_step_traffic.json")
   if os.path.exists(p):
     try:
-      return json.load(open(p)).get("dram_bytes_per_launch")
+      return json.load(open(p)).get("dram_bytes_per_step")
     except Exception:
       return None
   return None
@@ -201,7 +203,23 @@ def reference_graphs_per_s(budget_s=20.0):
     avail = len(os.sched_getaffinity(0))
   except Exception:
     avail = os.cpu_count() or 1
-  torch.set_num_threads(avail)      # all the host threads the reference can use
+  # "all the host threads it can use": torch's intra-op pool does not scale to every core for E = 400 000 rows x 256
+  # (128 threads were 5x SLOWER than 32 on the round-2 box), so the arm uses the thread count that runs ONE forward of a
+  # single TSP-500 instance fastest - the most favourable setting for the reference
+  p1, e1 = syn.tsp_sparse_batch(N_NODES, KNN, 1, seed=1)
+  x1 = torch.zeros(e1.shape[1], dtype=torch.int64)
+  best = None
+  with torch.no_grad():
+    for th in sorted({t for t in (8, 16, 32, 64, avail) if t <= avail}):
+      torch.set_num_threads(th)
+      t0 = time.perf_counter()
+      model.categorical_denoise_step(torch.from_numpy(p1), x1, np.array([500]).astype(int), torch.device("cpu"),
+                                     torch.from_numpy(e1), target_t=np.array([400]).astype(int))
+      dt = time.perf_counter() - t0
+      if best is None or dt < best[1]:
+        best = (th, dt)
+  avail = best[0]
+  torch.set_num_threads(avail)
   dev = torch.device("cpu")
   sched = RefSchedule(inference_schedule="cosine", T=T, inference_T=DENOISE_STEPS)
   with torch.no_grad():   # untimed warm-up on a tiny instance: thread pool, allocator, lazy imports
@@ -240,7 +258,7 @@ def run_reference(args, rank, world):
     sample = (f"unmodified reference (oracle/_ref: TSPModel.categorical_denoise_step = GNNEncoder.forward + "
               f"categorical_posterior, torch CPU fp32, stock gather-then-GEMM) on one block-diagonal batch of {BATCH} "
               f"TSP-500 k=50 instances, {steps_run} of {DENOISE_STEPS} denoise steps per timed step (~20 s), extrapolated "
-              f"x{DENOISE_STEPS / steps_run:.1f}; torch.set_num_threads({threads}) = all visible cores")
+              f"x{DENOISE_STEPS / steps_run:.1f}; torch.set_num_threads({threads}) = the fastest of 8/16/32/64/all visible cores on one forward")
   else:
     sample = (f"oracle port: 1 TSP-500 k=50 instance, {steps_run} of {DENOISE_STEPS} denoise steps per timed step, "
               f"extrapolated x{DENOISE_STEPS / steps_run:.1f}; thread count auto-picked ({threads})")
@@ -257,32 +275,93 @@ def run_reference(args, rank, world):
 
 
 # ------------------------------------------------------------------------------------------------
+# BASELINE.json configs.  configs[1] (C2) is the headline workload the default run times; --config C1|C3|C4|C5 time the
+# other ones through the same code path and print the same JSON schema (profiles/r02_other_configs.jsonl).
+CONFIGS = {
+    "C1": dict(task="tsp", nodes=50, knn=-1, batch=1, diffusion="categorical",
+               label="TSP-50 dense graph, categorical diffusion, 1 instance, 50 denoise steps (BASELINE configs[0])"),
+    "C2": dict(task="tsp", nodes=N_NODES, knn=KNN, batch=BATCH, diffusion="categorical", label=None),
+    "C3": dict(task="tsp", nodes=1000, knn=100, batch=8, diffusion="gaussian",
+               label="TSP-1000 sparse k=100, Gaussian diffusion, 50 denoise steps, batch 8 (BASELINE configs[2])"),
+    "C4": dict(task="mis", nodes=(700, 800), knn=0, batch=32, diffusion="categorical",
+               label="MIS ER-[700,800] p=0.15, categorical, 50 denoise steps, batch 32 (BASELINE configs[3])"),
+    "C5": dict(task="tsp", nodes=10000, knn=50, batch=4, diffusion="categorical",
+               label="TSP-10000 sparse k=50, categorical, 50 denoise steps, 4x parallel sampling per GPU (BASELINE configs[4])"),
+    "B1": dict(task="tsp", nodes=N_NODES, knn=KNN, batch=1, diffusion="categorical",
+               label="TSP-500 sparse k=50, categorical, 50 denoise steps, batch 1 (the reference test loader's shape)"),
+}
+
+
+def build_workload(cfg, rank):
+  """-> dict(points, edge_index, xt0, V, E, n_state, graphs, node_only, gn_segments, args)."""
+  from types import SimpleNamespace as NS
+  from difusco_b200 import synthetic as syn
+  a = model_args()
+  a.diffusion_type = cfg["diffusion"]
+  seed = 1234 + 1000 * rank
+  if cfg["task"] == "mis":
+    ei, sizes = syn.mis_batch(cfg["nodes"][0], cfg["nodes"][1], 0.15, cfg["batch"], seed=seed)
+    V, E = int(sum(sizes)), ei.shape[1]
+    xt0 = (syn.initial_noise(V, rank) > 0).astype(np.float32)
+    a.sparse_factor = -1
+    return dict(points=None, edge_index=ei, xt0=xt0, V=V, E=E, n_state=V, graphs=cfg["batch"], node_only=True,
+                gn_segments=1, args=a)
+  if cfg["knn"] <= 0:      # dense: the complete graph incl. self pairs, per-sample GroupNorm
+    n, B = cfg["nodes"], cfg["batch"]
+    pts = np.concatenate([syn.tsp_points(n, seed, i) for i in range(B)]).astype(np.float32)
+    ei = np.concatenate([syn.complete_edge_index(n) + i * n for i in range(B)], axis=1)
+    xt0 = (syn.initial_noise(ei.shape[1], rank) > 0).astype(np.float32)
+    a.sparse_factor = -1
+    return dict(points=pts, edge_index=ei, xt0=xt0, V=B * n, E=ei.shape[1], n_state=ei.shape[1], graphs=B,
+                node_only=False, gn_segments=B, args=a)
+  pts, ei = syn.tsp_sparse_batch(cfg["nodes"], cfg["knn"], cfg["batch"], seed=seed)
+  a.sparse_factor = cfg["knn"]
+  noise = syn.initial_noise(ei.shape[1], rank)
+  xt0 = (noise > 0).astype(np.float32) if cfg["diffusion"] == "categorical" else noise.astype(np.float32)
+  return dict(points=pts, edge_index=ei, xt0=xt0, V=pts.shape[0], E=ei.shape[1], n_state=ei.shape[1],
+              graphs=cfg["batch"], node_only=False, gn_segments=1, args=a)
+
+
+def algorithmic_bytes_per_step(wl):
+  """sparse / dense TSP 2 L E H 4 = 24 576 E per denoise step (L-1 inter-layer reads + the head's read,
+  L writes; layer 0 reads xt instead of a materialised e0); MIS (2L-2) E H 4 (no e0 read, the last layer's e is never
+  consumed) + 2 L V H 4 (the node stream)."""
+  if wl["node_only"]:
+    return (2 * L - 2) * wl["E"] * H * 4 + 2 * L * wl["V"] * H * 4
+  return 2 * L * wl["E"] * H * 4
+
+
 def run_ours(args, rank, world, local_rank):
   import torch
   import torch.distributed as dist
-  from difusco_b200 import _cabi, synthetic as syn
+  from difusco_b200 import _cabi
+  from difusco_b200.pl_mis_model import MISModel
   from difusco_b200.pl_tsp_model import TSPModel
+  from difusco_b200 import synthetic as syn
+  from difusco_b200.utils.diffusion_schedulers import InferenceSchedule
 
   torch.cuda.set_device(local_rank)
   dev = torch.device("cuda", local_rank)
   if world > 1:
     dist.init_process_group("nccl", device_id=dev)
-  model = TSPModel(model_args())
-  w = syn.make_encoder_weights(0, out_channels=2)
+  cfg = CONFIGS[args.config]
+  wl = build_workload(cfg, rank)
+  categorical = cfg["diffusion"] == "categorical"
+  model = (MISModel if wl["node_only"] else TSPModel)(wl["args"])
+  w = syn.make_encoder_weights(0, out_channels=2 if categorical else 1)
   model.model.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()})
   model.cuda(local_rank).eval()
-  if os.environ.get("DFB_EDGE_IMPL", "tc") == "fp32":
-    model.model.engine().set_edge_impl(_cabi.EDGE_IMPL_FP32)
-
-  # per-rank batch: different instances on every rank (seed offset), same shape
-  pts, ei = syn.tsp_sparse_batch(N_NODES, KNN, BATCH, seed=1234 + 1000 * rank)
-  V, E = pts.shape[0], ei.shape[1]
-  xt0 = (syn.initial_noise(E, rank) > 0).astype(np.float32)
-  d_pts, d_ei, d_xt0 = torch.from_numpy(pts).to(dev), torch.from_numpy(ei).to(dev), torch.from_numpy(xt0).to(dev)
   ctx = model.model.engine()
+  impl = os.environ.get("DFB_EDGE_IMPL", "tc")
+  if impl != "tc":
+    ctx.set_edge_impl({"fp32": _cabi.EDGE_IMPL_FP32, "tc1": _cabi.EDGE_IMPL_TC1}[impl])
   stream = torch.cuda.current_stream().cuda_stream
+  V, E, n_state, graphs = wl["V"], wl["E"], wl["n_state"], wl["graphs"]
+  d_ei = torch.from_numpy(wl["edge_index"]).to(dev)
+  d_xt0 = torch.from_numpy(wl["xt0"]).to(dev)
+  d_pts = torch.from_numpy(wl["points"]).to(dev) if wl["points"] is not None else None
+  mode = _cabi.CATEGORICAL if categorical else _cabi.GAUSSIAN
 
-  from difusco_b200.utils.diffusion_schedulers import InferenceSchedule
   sched = InferenceSchedule("cosine", T, DENOISE_STEPS)
   t1s, cs, ls = [], [], []
   for i in range(DENOISE_STEPS):
@@ -290,13 +369,15 @@ def run_ours(args, rank, world, local_rank):
     c, last = model.posterior_consts(int(t1), int(t2))
     t1s.append(int(t1)); cs.append(c); ls.append(last)
 
-  model._prepare(d_pts, d_ei, dev)
-  gathered = [torch.empty(E, device=dev) for _ in range(world)] if world > 1 else None
-  x = torch.empty(E, device=dev)
+  model.model.set_graph(d_ei, V, wl["gn_segments"])
+  if d_pts is not None:
+    model.model.set_points(d_pts)
+  gathered = [torch.empty(n_state, device=dev) for _ in range(world)] if world > 1 else None
+  x = torch.empty(n_state, device=dev)
 
   def one_step(seed):
     x.copy_(d_xt0)
-    ctx.denoise(_cabi.CATEGORICAL, x.data_ptr(), t1s, cs, ls, None, seed, stream)
+    ctx.denoise(mode, x.data_ptr(), t1s, cs, ls, None, seed, stream)
     if world > 1:
       dist.all_gather(gathered, x)
 
@@ -312,7 +393,6 @@ def run_ours(args, rank, world, local_rank):
   if rank == 0:
     sampler.start()
   launches0 = ctx.launch_count()
-  ctx.profile_begin()
   ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   ev0.record()
   for i in range(args.steps):
@@ -320,24 +400,40 @@ def run_ours(args, rank, world, local_rank):
   ev1.record()
   fence()
   ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
-  edge_ms, edge_n = ctx.profile_end()
   launches = ctx.launch_count() - launches0
   clocks = sampler.stop() if rank == 0 else None
   if world > 1:
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
   total_ms = float(ms.item())
   hm = x.cpu().numpy()
-  assert np.isfinite(hm).all() and hm.min() >= 0.0 and hm.max() <= 1.0 + 1e-5
+  assert np.isfinite(hm).all()
+  if categorical:
+    assert hm.min() >= 0.0 and hm.max() <= 1.0 + 1e-5
+
+  # ---- the dominant kernel on its own: ONE more batch with per-launch CUDA events on the launching stream (plain
+  #      launches: events cannot be recorded inside the captured graph the timed region replays); not part of `value`
+  ctx.set_graph_capture(False)
+  ctx.profile_begin()
+  one_step(999)
+  torch.cuda.synchronize()
+  edge_ms, edge_n = ctx.profile_end()
+  pev0, pev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  pev0.record()
+  one_step(998)
+  pev1.record()
+  torch.cuda.synchronize()
+  plain_ms = pev0.elapsed_time(pev1)
+  ctx.set_graph_capture(True)
 
   # ---- e2e: same metric through the host-buffer C-ABI call (H2D of inputs + D2H of the heatmap per step)
-  p_pts = torch.from_numpy(pts).pin_memory()
-  p_ei = torch.from_numpy(ei).pin_memory()
-  p_xt0 = torch.from_numpy(xt0).pin_memory()
-  p_hm = torch.empty(E, dtype=torch.float32).pin_memory()
+  p_ei = torch.from_numpy(wl["edge_index"]).pin_memory()
+  p_xt0 = torch.from_numpy(wl["xt0"]).pin_memory()
+  p_pts = torch.from_numpy(wl["points"]).pin_memory() if wl["points"] is not None else None
+  p_hm = torch.empty(n_state, dtype=torch.float32).pin_memory()
 
   def e2e_step(seed):
-    ctx.denoise_host(_cabi.CATEGORICAL, p_pts.data_ptr(), p_ei.data_ptr(), V, E, 1, p_xt0.data_ptr(), t1s, cs, ls,
-                     seed, p_hm.data_ptr(), stream)
+    ctx.denoise_host(mode, p_pts.data_ptr() if p_pts is not None else None, p_ei.data_ptr(), V, E, wl["gn_segments"],
+                     p_xt0.data_ptr(), t1s, cs, ls, seed, p_hm.data_ptr(), stream)
   e2e_step(0)
   fence()
   t0 = time.perf_counter()
@@ -347,31 +443,47 @@ def run_ours(args, rank, world, local_rank):
   e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
   if world > 1:
     dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-  e2e_value = BATCH * world * args.steps / float(e2e_s.item())
-  h2d = pts.nbytes + ei.nbytes + xt0.nbytes
+  e2e_value = graphs * world * args.steps / float(e2e_s.item())
+  h2d = wl["edge_index"].nbytes + wl["xt0"].nbytes + (wl["points"].nbytes if wl["points"] is not None else 0)
   d2h = p_hm.numel() * 4
 
   if rank == 0:
-    value = BATCH * world * args.steps / (total_ms / 1e3)
+    value = graphs * world * args.steps / (total_ms / 1e3)
     peak, peak_src = measured_peaks()
-    # algorithmic bytes per fused edge-layer launch: E*H*4 write every layer, E*H*4 read for
-    # layers 1..L-1 (layer 0 reads the 2-row LUT); the head's read of the last e is booked to the head kernel.
-    alg_bytes_total = (2 * L - 1) * E * H * 4 * DENOISE_STEPS * args.steps
-    achieved = alg_bytes_total / (edge_ms / 1e3) / 1e9 if edge_ms > 0 else 0.0
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+    # whole-step accounting: every launch of a denoise step is inside the number, nothing is booked elsewhere
+    step_bytes = algorithmic_bytes_per_step(wl)
+    achieved = step_bytes * DENOISE_STEPS * args.steps / (total_ms / 1e3) / 1e9
+    n_layer_launches = max(int(edge_n), 1)
+    per_launch_bytes = ((2 * L - 1) * E * H * 4 / L) if not wl["node_only"] else (2 * L - 2) * E * H * 4 / L
+    k_ms = edge_ms / n_layer_launches
+    k_achieved = per_launch_bytes / (k_ms / 1e3) / 1e9 if k_ms > 0 else 0.0
+    wlc = workload_config(world)
+    if cfg["label"]:
+      wlc["workload"] = cfg["label"] + ", per GPU"
+      wlc.update(nodes_per_graph=cfg["nodes"], knn=cfg["knn"], batch_per_gpu=cfg["batch"], global_batch=cfg["batch"] * world)
+      wlc["l2_policy"] = (f"edge stream {E * H * 4 / 1e6:.0f} MB per GPU" +
+                          (" exceeds the 126 MB L2" if E * H * 4 > 126e6 else " fits the 126 MB L2 (no flush: the loop streams it 24x per step)"))
+    line = {"metric": METRIC if args.config == "C2" else f"{args.config} graphs/sec, 50-step denoise ({cfg['label']})",
+            "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32 (3-term bf16 split on tcgen05, fp32 accumulate)",
-            "data": "synthetic", "config": workload_config(world),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
-                         "kernel": ("k_edge_layer_tc16w" if os.environ.get("DFB_TC_WPQ", "4") == "4" else "k_edge_layer_tc<%s>" % os.environ.get("DFB_TC_WPQ"))
-                                   if os.environ.get("DFB_EDGE_IMPL", "tc") != "fp32" else "k_edge_layer_fp32",
-                         "algorithmic_bytes_per_launch": (2 * L - 1) * E * H * 4 / L,
-                         "launches_timed": int(edge_n), "kernel_ms_total": edge_ms,
-                         "kernel_share_of_step": edge_ms / total_ms},
+            "data": "synthetic", "config": wlc,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": ncu_traffic(), "peak_source": peak_src,
+                         "scope": "whole denoise step: every launch of the timed loop (CUDA-graph replay), timed with CUDA "
+                                  "events around the loop; algorithmic bytes = SURVEY 8(d) per step",
+                         "algorithmic_bytes_per_step": step_bytes, "denoise_steps_timed": DENOISE_STEPS * args.steps,
+                         "kernel": {"name": "k_edge_layer_pair (CTA-pair fused edge layer; layer 0 and the MIS last layer: "
+                                            "k_edge_layer_tc16w)" if impl == "tc" else impl,
+                                    "algorithmic_bytes_per_launch": per_launch_bytes, "launches_timed": int(edge_n),
+                                    "ms_per_launch": k_ms, "achieved": k_achieved, "frac": k_achieved / peak,
+                                    "share_of_step": edge_ms / plain_ms if plain_ms > 0 else None,
+                                    "how": "per-launch CUDA events on the launching stream over one extra batch with plain "
+                                           "launches (events cannot be recorded inside the replayed graph)"}},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-            "gpu_launches": int(launches), "clocks": clocks}
-    if world == 1 and not args.no_cpu_baseline:
+            "gpu_launches": int(launches), "launches_per_denoise_step": launches / (DENOISE_STEPS * args.steps),
+            "graph_replay_vs_plain_launches_ms": [total_ms / args.steps, plain_ms], "clocks": clocks}
+    if world == 1 and not args.no_cpu_baseline and args.config == "C2":
       r = reference_graphs_per_s(budget_s=20.0)
       if r is not None:
         v, dt, threads, n_run = r
@@ -398,6 +510,7 @@ def main():
   ap.add_argument("--steps", type=int, default=3)
   ap.add_argument("--warmup", type=int, default=3)
   ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+  ap.add_argument("--config", default="C2", choices=sorted(CONFIGS), help="BASELINE.json config (default C2 = configs[1], the headline)")
   ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
   args = ap.parse_args()
   rank = int(os.environ.get("RANK", "0"))

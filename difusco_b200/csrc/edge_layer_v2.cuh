@@ -121,12 +121,39 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
     }
   }
 }
+// L2 eviction policies: the edge stream passes through L2 once per layer (evict_first), the node tensor uvab (32 MB at C2)
+// and the weights (1 MB) are re-read by every tile (evict_last) - without the hints the 820 MB/launch stream pushes
+// part of uvab out of the 126 MB L2 (ncu: +117 MB of DRAM reads per launch).
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
 // TMA load whose completion is booked on the leader CTA's barrier (cute SM100_TMA_2SM_LOAD_2D)
-__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint64_t pol) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & PEER_MASK), "r"(c0), "r"(c1)
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & PEER_MASK), "r"(c0), "r"(c1), "l"(pol)
       : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_hint(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(pol)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* map, uint32_t src, int c0, int c1, uint64_t pol) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async16_hint(uint32_t dst_smem, const void* src, uint64_t pol) {
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
   asm volatile(
@@ -250,6 +277,7 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
     // ===================================== weight TMA (both CTAs, each its N-half) =====================================
     if (lane == 0) {
       const int n_use = debug ? 8 : 16;
+      const uint64_t pol_keep = l2_policy_evict_last();
       uint32_t u = 0;
       for (int it = 0; it < n_my; ++it) {
         for (int i = 0; i < n_use; ++i, ++u) {
@@ -259,8 +287,8 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
           const uint32_t dst = smem_base + OFF_B + sb * STAGE;
           // arena rows of a layer: C_hi | C_lo | O_hi | O_lo (256 each); this CTA's output channels are rows rank*128..+127
           const int rb = P.w_row_base + (i < 8 ? 0 : 512) + (int)rank * 128, kc = (i & 7) * 32;
-          tma_load_2d_pair(dst, &wmap, &b_full[sb], kc, rb);
-          tma_load_2d_pair(dst + HALF, &wmap, &b_full[sb], kc, rb + 256);
+          tma_load_2d_pair(dst, &wmap, &b_full[sb], kc, rb, pol_keep);
+          tma_load_2d_pair(dst + HALF, &wmap, &b_full[sb], kc, rb + 256, pol_keep);
         }
       }
     }
@@ -339,6 +367,7 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
   } else if (warp == 2) {
     // ===================================== edge endpoints + input boxes =====================================
     uint32_t ga = 0;
+    const uint64_t pol_stream = l2_policy_evict_first();
     for (int it = 0; it < n_my; ++it) {
       const int tile = tile_of(it), ib = it & 1;
       if (it >= 2) mbar_wait(&idx_free[ib], ((it >> 1) - 1) & 1, P.error_flag, 20);
@@ -361,13 +390,14 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
         if (it + 1 < n_my && tile_of(it + 1) < P.n_tiles && !(P.probe & 256)) {
           // the next tile's 128 edge rows are one contiguous 128 KB block: pull it into L2 now
           const float* nxt = P.e + (size_t)tile_of(it + 1) * TC_TILE * H;
-          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nxt), "r"(TC_TILE * H * 4) : "memory");
+          asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(nxt), "r"(TC_TILE * H * 4), "l"(pol_stream)
+                       : "memory");
         }
         for (int b = 0; b < 8; ++b, ++ga) {
           const uint32_t sa = ga % NA;
           mbar_wait(&a_empty[sa], ((ga / NA) & 1) ^ 1, P.error_flag, 4);
           mbar_arrive_expect_tx(&box_full[b], STAGE);
-          tma_load_2d(smem_base + OFF_A + sa * STAGE, &emap, &box_full[b], 32 * b, tile * TC_TILE);
+          tma_load_2d_hint(smem_base + OFF_A + sa * STAGE, &emap, &box_full[b], 32 * b, tile * TC_TILE, pol_stream);
         }
       }
       __syncwarp();
@@ -377,12 +407,13 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
     // part p stages box p, then box p + 4 of a tile in its own gather buffers; the store is issued here and the part is told
     // when the staging has been read
     if (lane == 0 && !debug) {
+      const uint64_t pol_stream = l2_policy_evict_first();
       int pending = -1;   // part whose store was issued last and whose staging has not been released yet
       for (int it = 0; it < n_my; ++it) {
         for (int j = 0; j < 2; ++j) {
           for (int p2 = 0; p2 < 4; ++p2) {
             mbar_wait(&out_full[p2], j, P.error_flag, 8);   // two phases per tile: parity == j
-            tma_store_2d(&emap, smem_base + OFF_G + p2 * PART_G, 32 * (p2 + 4 * j), tile_of(it) * TC_TILE);
+            tma_store_2d_hint(&emap, smem_base + OFF_G + p2 * PART_G, 32 * (p2 + 4 * j), tile_of(it) * TC_TILE, pol_stream);
             tma_store_commit();
             if (pending >= 0) {          // the store before this one has been read once at most one group is pending
               tma_store_wait_read_n<1>();
@@ -411,7 +442,14 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
     const uint32_t t_acc1 = tmem_base + ((uint32_t)(wq * 32) << 16);
     const uint32_t t_acc2 = t_acc1 + 256u;
     auto worker_bar = [] { asm volatile("bar.sync 1, %0;" ::"n"(NWORK) : "memory"); };
-    auto part_bar = [&] { asm volatile("bar.sync %0, 128;" ::"r"(2 + part) : "memory"); };
+    auto part_bar = [&] {   // the four warps of this part; immediate barrier ids (tools such as racecheck model those)
+      switch (part) {
+        case 0: asm volatile("bar.sync 2, 128;" ::: "memory"); break;
+        case 1: asm volatile("bar.sync 3, 128;" ::: "memory"); break;
+        case 2: asm volatile("bar.sync 4, 128;" ::: "memory"); break;
+        default: asm volatile("bar.sync 5, 128;" ::: "memory"); break;
+      }
+    };
     auto stat_buf = [&](int p2) { return reinterpret_cast<float*>(smem + OFF_G + (p2 * 4 + wq) * 2 * GBUF); };
 #ifdef DFB_PHASE_PROF
     const bool prof = (P.probe & 128) && ww == 0 && lane == 0;
@@ -423,6 +461,7 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
 #define XSUB(i) do { } while (0)
 #endif
     uint32_t gbox = 0;   // global input-box counter of this CTA (operand ring position)
+    const uint64_t pol_keep = l2_policy_evict_last();
     bool prev_valid = false;   // this thread's row of the previous tile is a real edge (GroupNorm statistics)
     for (int it = 0; it <= n_my; ++it) {
       const bool have_tile = it < n_my;      // X phase converts tile `it` and finishes (E4) tile `it - 1`
@@ -581,8 +620,8 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
 #endif
         const uint32_t b32 = smem_u32(buf);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) cp_async16(b32 + j * 512 + goff, gptr[j] + step * 8);
-        if (bptr) cp_async16(b32 + 2048 + lane * 16, bptr + step * 8);
+        for (int j = 0; j < 4; ++j) cp_async16_hint(b32 + j * 512 + goff, gptr[j] + step * 8, pol_keep);
+        if (bptr) cp_async16_hint(b32 + 2048 + lane * 16, bptr + step * 8, pol_keep);
         cp_async_commit();
       };
       XSUB(5);   // endpoints, segments, gather pointers

@@ -69,8 +69,7 @@ def merge_tours(adj_mat, np_points, edge_index_np, sparse_graph=False, parallel_
   points = np.asarray(np_points)
   n = points.shape[0]
   pts64 = points.astype("double")
-  tours, iterations = [], []
-  for part in np.split(np.asarray(adj_mat), parallel_sampling, axis=0):
+  def one(part):
     if sparse_graph:
       edge_index, heat = np.asarray(edge_index_np), part.reshape(-1)
     else:                         # adj_mat[0] + adj_mat[0].T  ==  both orientations of the complete graph
@@ -83,8 +82,19 @@ def merge_tours(adj_mat, np_points, edge_index_np, sparse_graph=False, parallel_
       status, tour, it = _cabi.tsp_merge_sparse(pts64, heat, edge_index, mode=0 if exact else 1)
     if status != _cabi.MERGE_COMPLETE:
       tour, it = _cabi.tsp_merge_order(n, _dense_order(points, heat, edge_index))
-    tours.append([int(v) for v in tour])
-    iterations.append(it)
+    return [int(v) for v in tour], it
+
+  parts = np.split(np.asarray(adj_mat), parallel_sampling, axis=0)
+  if n > 1000 and parallel_sampling > 1:
+    # tsp_utils.py:121-126 runs the samples in a multiprocessing.Pool(parallel_sampling); the C++ merge releases the GIL
+    # (ctypes), so a thread pool gives the same parallelism without pickling the heat maps
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=parallel_sampling) as pool:
+      results = list(pool.map(one, parts))
+  else:
+    results = [one(part) for part in parts]
+  tours = [r[0] for r in results]
+  iterations = [r[1] for r in results]
   return tours, np.mean(iterations)
 
 

@@ -254,3 +254,26 @@ def test_fused_loop_graph_capture_matches_plain_launches(weights2):
   c1 = m.denoise_heatmap(G.cu(pts2), G.cu(ei2), G.cu(x2), seed=9).cpu().numpy()
   a4 = m.denoise_heatmap(G.cu(pts), G.cu(ei), G.cu(xt0), seed=5).cpu().numpy()
   assert np.array_equal(a1, a4) and np.isfinite(c1).all()
+
+
+# ------------------------------------------------------------------------------------------------
+# N-GPU sharding on real GPUs (NCCL): per-instance heat maps bitwise equal to the single-GPU answer
+# ------------------------------------------------------------------------------------------------
+def test_multi_gpu_sharding_bitwise_equal_to_single_gpu():
+  import os
+  import socket
+  import subprocess
+  import sys
+  n = torch.cuda.device_count()
+  if n < 2:
+    pytest.skip("needs >= 2 GPUs (run under `gpurun --gpus 2`; log committed as profiles/r02_multi_gpu_check.txt)")
+  s = socket.socket()
+  s.bind(("127.0.0.1", 0))
+  port = s.getsockname()[1]
+  s.close()
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={min(n, 2)}",
+                      "--master-addr", "127.0.0.1", "--master-port", str(port),
+                      os.path.join(root, "scripts", "multi_gpu_check.py")], capture_output=True, text=True, timeout=900)
+  assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+  assert '"bitwise_equal_to_single_gpu": true' in r.stdout

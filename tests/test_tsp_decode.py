@@ -288,3 +288,21 @@ def test_merge_tours_equals_oracle_on_random_graphs():
     fast, _ = (tu.merge_tours(heat, pts, None, sparse_graph=False, parallel_sampling=2, exact=False) if case % 3 == 0
                else tu.merge_tours(heat, pts, ei, sparse_graph=True, exact=False))
     assert all(is_tour(t, n) for t in fast), case      # the nearest-end completion always yields a Hamiltonian cycle
+
+
+def test_merge_parallel_sampling_thread_pool_equals_sequential():
+  """tsp_utils.py:121-126: more than 1000 nodes and parallel_sampling > 1 -> the samples are merged concurrently (thread
+  pool around the GIL-free C++ merge); the tours must be the ones the sequential path gives, in the same order."""
+  from sklearn.neighbors import KDTree
+  rng = np.random.default_rng(7)
+  n, k, P = 1200, 8, 3
+  pts = rng.random((n, 2))
+  _, idx = KDTree(pts).query(pts, k=k)
+  ei = np.stack([np.repeat(np.arange(n), k), idx.reshape(-1)]).astype(np.int64)
+  heat = rng.random((P, n * k)).astype(np.float32)
+  par_tours, par_it = tu.merge_tours(heat, pts, ei, sparse_graph=True, parallel_sampling=P, exact=False)
+  seq = [tu.merge_tours(heat[p:p + 1], pts, ei, sparse_graph=True, parallel_sampling=1, exact=False) for p in range(P)]
+  assert par_tours == [s[0][0] for s in seq]
+  assert np.isclose(par_it, np.mean([s[1] for s in seq]))
+  for t in par_tours:
+    assert len(t) == n + 1 and t[0] == t[-1] and sorted(t[:-1]) == list(range(n))
