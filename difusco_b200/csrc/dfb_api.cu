@@ -43,6 +43,7 @@ struct dfb_ctx {
   const float *Wt_node = nullptr, *b_node = nullptr, *Wt_edge = nullptr, *b_edge = nullptr;
   const float *dimt128 = nullptr, *dimt256 = nullptr;
   float* lut = nullptr;   // [2][256] categorical edge-embedding LUT (inside wbuf)
+  float* cl0 = nullptr;   // [2][256] C_0 * lut (layer 0's GEMM1 by table lookup); followed by [2][256] zeros for the MIS e0 = 0 case
   // ---- graph ----
   bool graph_ready = false, points_ready = false;
   GraphDev g{};
@@ -410,7 +411,7 @@ extern "C" int dfb_load_weights(dfb_ctx* ctx, int n_layers, int hidden_dim, int 
 
   // frequency tables: computed by the Python host with the reference's own torch expressions and
   // passed as pseudo-tensors when available (bit-identical tables); otherwise computed here.
-  size_t o_freqs = put(TE), o_d128 = put(TE), o_d256 = put(H), o_lut = put(2 * H);
+  size_t o_freqs = put(TE), o_d128 = put(TE), o_d256 = put(H), o_lut = put(2 * H), o_cl0 = put(4 * H);
   auto it = sd.find("__const.time_freqs");
   for (int m = 0; m < TE; ++m)
     arena[o_freqs + m] = (it != sd.end() && it->second.second == TE)
@@ -455,6 +456,7 @@ extern "C" int dfb_load_weights(dfb_ctx* ctx, int n_layers, int hidden_dim, int 
   ctx->hp.out_channels = out_channels;
   ctx->dimt128 = base + o_d128; ctx->dimt256 = base + o_d256;
   ctx->lut = (float*)ctx->wbuf.p + o_lut;
+  ctx->cl0 = (float*)ctx->wbuf.p + o_cl0;   // second half stays zero (arena slots are zero-initialised)
   ctx->L = L; ctx->out_channels = out_channels; ctx->node_only = node_feature_only;
 
   int r = tc_bind_weights(&ctx->tc, ctx->layers.data(), L);
@@ -471,6 +473,9 @@ extern "C" int dfb_load_weights(dfb_ctx* ctx, int n_layers, int hidden_dim, int 
     k_scalar_features<<<2, H>>>((const float*)ctx->tvals.p, nullptr, ctx->dimt256, (float*)ctx->feat.p, 2);
     CKL(ctx);
     k_linear<<<dim3(1, 1), 256>>>((const float*)ctx->feat.p, ctx->Wt_edge, ctx->b_edge, ctx->lut, 2, H);
+    CKL(ctx);
+    // layer 0 never needs its GEMM1: C_0 applied to the two possible input rows (fp32 FFMA; b_C rides in B h's bias)
+    k_linear<<<dim3(1, 1), 256>>>(ctx->lut, ctx->layers[0].Wt_C, nullptr, ctx->cl0, 2, H);
     CKL(ctx);
     CK(ctx, cudaDeviceSynchronize());
   }
@@ -699,10 +704,15 @@ static int launch_edge_layer(dfb_ctx* ctx, int l, const float* uvab, const float
                                                             ctx->g, ctx->layers[l], tvec_edge, write_e,
                                                             ctx->agg_mode);
     CKL(ctx);
-  } else if (ctx->edge_impl == DFB_EDGE_IMPL_TC && ctx->pair_enabled && ctx->max_seg <= v2::MAXSEG && write_e && !e_zero && !xt_for_lut) {
-    // a middle layer (reads and writes the edge stream): the CTA-pair kernel
+  } else if (ctx->edge_impl == DFB_EDGE_IMPL_TC && ctx->pair_enabled && ctx->max_seg <= v2::MAXSEG && write_e &&
+             (!(e_zero || xt_for_lut) || ctx->L > 1)) {
+    // the CTA-pair kernel: middle layers read and write the edge stream; layer 0 (table rows in) runs in LUT mode
+    const bool lut_mode = e_zero || xt_for_lut;
+    const float* cl = lut_mode ? (e_zero ? ctx->cl0 + 2 * H : ctx->cl0) : nullptr;       // e0 = 0: zero tables
+    const float* lut = lut_mode ? (e_zero ? ctx->cl0 + 2 * H : ctx->lut) : nullptr;
     int r = v2::launch(&ctx->pair, &ctx->tc, l, (float*)ctx->e.p, uvab, (float*)ctx->partials.p, ctx->g, ctx->layers[l],
-                       tvec_edge, ctx->agg_mode, st, gn_blocks ? (double*)ctx->gn_part.p : nullptr, gn_blocks);
+                       tvec_edge, ctx->agg_mode, st, gn_blocks ? (double*)ctx->gn_part.p : nullptr, gn_blocks,
+                       xt_for_lut, cl, lut);
     if (r) FAIL(ctx, DFB_E_CUDA, "tcgen05 pair edge layer: %s", ctx->tc.err.c_str());
     ctx->launches += ctx->tc.last_launches;
   } else {

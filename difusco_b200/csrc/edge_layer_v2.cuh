@@ -50,7 +50,8 @@ constexpr int IDX_INTS = 2 * TC_TILE + 8;            // row[128] | col[128] | gr
 constexpr int OFF_GN = OFF_IDX + 2 * IDX_INTS * 4;   // per worker warp: 8 doubles (4 groups x {sum, sum of squares}) x 2 boxes
 constexpr int OFF_SEG = OFF_GN + NWORKW * 16 * 8;      // per worker warp: node of each of its (<= MAXSEG) segments
 constexpr int OFF_BAR = OFF_SEG + NWORKW * MAXSEG * 4;
-constexpr int SMEM_BYTES = OFF_BAR + 48 * 8;
+constexpr int SMEM_BYTES = OFF_BAR + 52 * 8;
+static_assert(NA <= 6 && NB <= 6, "barrier slots");
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 static_assert(GBUF % 128 == 0, "gather buffers stay 128-byte aligned");
 static_assert(PART_G >= STAGE && PART_G % 1024 == 0 && OFF_G % 1024 == 0, "a part's gather buffers hold one 128B-swizzled fp32 box");
@@ -67,6 +68,11 @@ struct Params {
   LayerParams lp;
   const float* tvec;      // [256] time vector added on edges (TSP) or nullptr (MIS)
   const float* zero_row;  // [1024] zeros: gather source of rows past the end of the edge list
+  // LUT mode (layer 0: the input rows are one of two table rows): per-edge selector in caller edge order (or
+  // null: always row 0, the MIS e0 = 0 case), cl = C * lut (GEMM1 by table lookup), lut = the residual rows
+  const float* lut_x;
+  const float* cl;        // [2][256]
+  const float* lut;       // [2][256]
   float* debug_acc;       // tests: dump the GEMM1 accumulator [E][256] and stop
   double* gn_part;        // last layer (sparse TSP head): per-(CTA, lane quarter) GroupNorm(32) partial sums [blocks][32][2], or null
   int E;                  // number of valid edge rows (GroupNorm statistics skip the padding rows)
@@ -207,9 +213,12 @@ __device__ __forceinline__ uint32_t sw64_off(int r, int j) {
 // general masked reduce; the sum / mean instantiation (the reference default) carries none of that code.
 // GNSTATS: the last layer of the sparse TSP encoder also leaves the head's GroupNorm partial sums (own instantiation: the
 // extra live values would otherwise cost the other eleven layers registers in the X phase).
-template <bool MAXAGG, bool GNSTATS>
+enum { MODE_PLAIN = 0, MODE_GN = 1, MODE_LUT = 2 };
+template <bool MAXAGG, int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap emap, const Params P) {
+  constexpr bool GNSTATS = MODE == MODE_GN;
+  constexpr bool LUT = MODE == MODE_LUT;   // no GEMM1, no input boxes: acc1 and the residual come from two-row tables
   extern __shared__ __align__(1024) unsigned char smem[];
   float* prm = reinterpret_cast<float*>(smem + OFF_PRM);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
@@ -218,16 +227,16 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
   // box b is always converted by the same part (b & 3).
   uint64_t* box_full = bars;        // [8]  TMA input box b of the tile landed (local, tx)
   uint64_t* a_full = bars + 8;      // [NA] LEADER: stage converted by both CTAs (4 warps each)
-  uint64_t* a_empty = bars + 13;    // [NA] MMA commit (multicast): stage consumed
-  uint64_t* b_full = bars + 18;     // [NB] LEADER: both weight halves landed (tx)
-  uint64_t* b_empty = bars + 22;    // [NB] MMA commit (multicast)
-  uint64_t* acc_rdy = bars + 26;    // [2]  MMA commit (multicast): GEMM1 / GEMM2 accumulator complete
-  uint64_t* a2_full = bars + 28;    // [4]  LEADER: GEMM2 A chunk (64 columns of s) written to TMEM by both CTAs
-  uint64_t* out_full = bars + 32;   // [4]  part p wrote a result box into its staging (4 warps)
-  uint64_t* stage_free = bars + 36; // [4]  the TMA store has read part p's staging (I/O warp)
-  uint64_t* idx_full = bars + 40;   // [2]  edge endpoints of a tile in shared memory (32 lanes of warp 2)
-  uint64_t* idx_free = bars + 42;   // [2]  the 16 worker warps are done with them
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 44);
+  uint64_t* a_empty = bars + 14;    // [NA] MMA commit (multicast): stage consumed
+  uint64_t* b_full = bars + 20;     // [NB] LEADER: both weight halves landed (tx)
+  uint64_t* b_empty = bars + 26;    // [NB] MMA commit (multicast)
+  uint64_t* acc_rdy = bars + 32;    // [2]  MMA commit (multicast): GEMM1 / GEMM2 accumulator complete
+  uint64_t* a2_full = bars + 34;    // [4]  LEADER: GEMM2 A chunk (64 columns of s) written to TMEM by both CTAs
+  uint64_t* out_full = bars + 38;   // [4]  part p wrote a result box into its staging (4 warps)
+  uint64_t* stage_free = bars + 42; // [4]  the TMA store has read part p's staging (I/O warp)
+  uint64_t* idx_full = bars + 46;   // [2]  edge endpoints of a tile in shared memory (32 lanes of warp 2)
+  uint64_t* idx_free = bars + 48;   // [2]  the 16 worker warps are done with them
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 50);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -276,11 +285,11 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
   if (warp == 0) {
     // ===================================== weight TMA (both CTAs, each its N-half) =====================================
     if (lane == 0) {
-      const int n_use = debug ? 8 : 16;
+      const int i_lo = LUT ? 8 : 0, n_use = debug ? 8 : 16;
       const uint64_t pol_keep = l2_policy_evict_last();
       uint32_t u = 0;
       for (int it = 0; it < n_my; ++it) {
-        for (int i = 0; i < n_use; ++i, ++u) {
+        for (int i = i_lo; i < n_use; ++i, ++u) {
           const uint32_t sb = u % NB, k = u / NB;
           mbar_wait(&b_empty[sb], (k & 1) ^ 1, P.error_flag, 1);
           if (leader) mbar_arrive_expect_tx(&b_full[sb], 2 * STAGE);
@@ -305,8 +314,8 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
 #define MMA_T1(acc) do { } while (0)
 #endif
       for (int it = 0; it < n_my; ++it) {
-        // ---- GEMM1: acc1 = e C^T, 8 K-chunks of 32, A and B from shared memory ----
-        for (int kc = 0; kc < 8; ++kc, ++ub, ++ga) {
+        // ---- GEMM1: acc1 = e C^T, 8 K-chunks of 32, A and B from shared memory (LUT mode: the workers fill acc1) ----
+        for (int kc = 0; kc < (LUT ? 0 : 8); ++kc, ++ub, ++ga) {
           const uint32_t sb = ub % NB, sa = ga % NA;
           MMA_T0();
           mbar_wait(&b_full[sb], (ub / NB) & 1, P.error_flag, 2);
@@ -328,7 +337,7 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
           umma2_commit(&a_empty[sa]);
           umma2_commit(&b_empty[sb]);
         }
-        umma2_commit(&acc_rdy[0]);
+        if (!LUT) umma2_commit(&acc_rdy[0]);
         if (debug) continue;
         // ---- GEMM2: acc2 += s O^T on top of the preloaded residual e + b_O; A operand (bf16 hi/lo of s) in TMEM:
         //      k-step j at columns 16 j (8 hi + 8 lo) ----
@@ -378,7 +387,10 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
         const int rr = j * 32 + lane, s_edge = tile * TC_TILE + rr;
         const bool ok = tile < P.n_tiles && s_edge < P.g.E;
         s_row[rr] = ok ? __ldg(P.g.row + s_edge) : -1;
-        s_col[rr] = ok ? __ldg(P.g.col + s_edge) : -1;
+        int cv = ok ? __ldg(P.g.col + s_edge) : -1;
+        if (LUT && ok && P.lut_x)   // table-row selector of the edge rides in bit 30 of its column index
+          cv |= (__ldg(P.lut_x + (P.g.perm ? __ldg(P.g.perm + s_edge) : s_edge)) != 0.0f) ? (1 << 30) : 0;
+        s_col[rr] = cv;
       }
       if (lane < 8) {   // (32-edge group, node) pair bookkeeping of the tile's four groups
         const int grp = tile * 4 + (lane & 3);
@@ -387,13 +399,13 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
       }
       mbar_arrive(&idx_full[ib]);
       if (lane == 0) {
-        if (it + 1 < n_my && tile_of(it + 1) < P.n_tiles && !(P.probe & 256)) {
+        if (!LUT && it + 1 < n_my && tile_of(it + 1) < P.n_tiles && !(P.probe & 256)) {
           // the next tile's 128 edge rows are one contiguous 128 KB block: pull it into L2 now
           const float* nxt = P.e + (size_t)tile_of(it + 1) * TC_TILE * H;
           asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(nxt), "r"(TC_TILE * H * 4), "l"(pol_stream)
                        : "memory");
         }
-        for (int b = 0; b < 8; ++b, ++ga) {
+        for (int b = 0; b < (LUT ? 0 : 8); ++b, ++ga) {
           const uint32_t sa = ga % NA;
           mbar_wait(&a_empty[sa], ((ga / NA) & 1) ^ 1, P.error_flag, 4);
           mbar_arrive_expect_tx(&box_full[b], STAGE);
@@ -475,10 +487,20 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
 #ifdef DFB_PHASE_PROF
       if (prof) tx = clock64();
 #endif
+      int xsel = 0;   // LUT mode: table row of this thread's edge
+      if (LUT && have_tile) {
+        mbar_wait(&idx_full[it & 1], (it >> 1) & 1, P.error_flag, 22);
+        const int cv = (reinterpret_cast<const int*>(smem + OFF_IDX) + (it & 1) * IDX_INTS + TC_TILE)[r];
+        xsel = (cv >= 0) ? ((cv >> 30) & 1) : 0;
+      }
       for (int j = 0; j < 2; ++j) {
         const int b = part + 4 * j;
         float4 xin[8];
-        if (have_tile) {
+        if (LUT && have_tile) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) xin[q] = __ldg(reinterpret_cast<const float4*>(P.lut + xsel * H + 32 * b) + q);
+        }
+        if (!LUT && have_tile) {
           const uint32_t g = gbox + b, sa = g % NA;
           mbar_wait(&box_full[b], it & 1, P.error_flag, 5);
           XSUB(0);   // wait for the input box
@@ -578,6 +600,22 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
       }
       gbox += 8;
       if (!have_tile) break;
+      if (LUT) {
+        // GEMM1 by table lookup: acc1[row][cbase .. cbase + 63] = (C lut[x])[...]  (GEMM2 of the previous tile, the last
+        // reader of these columns, completed before the E4 above)
+#pragma unroll
+        for (int hh = 0; hh < 4; ++hh) {
+          uint32_t v[16];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 c4 = __ldg(reinterpret_cast<const float4*>(P.cl + xsel * H + cbase + 16 * hh) + q);
+            v[4 * q] = __float_as_uint(c4.x); v[4 * q + 1] = __float_as_uint(c4.y);
+            v[4 * q + 2] = __float_as_uint(c4.z); v[4 * q + 3] = __float_as_uint(c4.w);
+          }
+          tmem_st16(t_acc1 + cbase + 16 * hh, v);
+        }
+        tmem_wait_st();
+      }
 
       // ---- this tile's edge endpoints, node segments, gather pointers ----
       const int ib = it & 1;
@@ -599,7 +637,8 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
       // past the end of the edge list gather zeros: their messages are exactly 0 (sum / mean) without a select
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int cj = s_col[wq * 32 + j * 8 + (lane >> 2)], uu = lane & 3;
+        const int cv = s_col[wq * 32 + j * 8 + (lane >> 2)], uu = lane & 3;
+        const int cj = (cv >= 0) ? (cv & 0x3fffffff) : -1;
         gptr[j] = (cj >= 0) ? P.uvab + (size_t)cj * 4 * H + ((uu < 2) ? 2 * H : H) + cbase + (uu & 1) * 4
                             : P.zero_row + ((uu < 2) ? 2 * H : H) + cbase + (uu & 1) * 4;
       }
@@ -634,8 +673,10 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
       PHASE(0);   // X phase
       const int s_edge = tile * TC_TILE + r;
       prev_valid = valid;
-      mbar_wait(&acc_rdy[0], it & 1, P.error_flag, 6);
-      tc_fence_after();
+      if (!LUT) {
+        mbar_wait(&acc_rdy[0], it & 1, P.error_flag, 6);
+        tc_fence_after();
+      }
       PHASE(1);   // wait for GEMM1
       if (debug) {
 #pragma unroll 1
@@ -968,13 +1009,12 @@ struct State {
 };
 
 inline int init(State* st, TcState* tc) {
-  cudaError_t e = cudaFuncSetAttribute(k_edge_layer_pair<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(k_edge_layer_pair<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(k_edge_layer_pair<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(k_edge_layer_pair<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  cudaError_t e = cudaSuccess;
+  const void* fns[6] = {(const void*)k_edge_layer_pair<false, MODE_PLAIN>, (const void*)k_edge_layer_pair<false, MODE_GN>,
+                        (const void*)k_edge_layer_pair<false, MODE_LUT>, (const void*)k_edge_layer_pair<true, MODE_PLAIN>,
+                        (const void*)k_edge_layer_pair<true, MODE_GN>, (const void*)k_edge_layer_pair<true, MODE_LUT>};
+  for (int i = 0; i < 6 && e == cudaSuccess; ++i)
+    e = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   if (e != cudaSuccess) {
     tc->err = std::string("cudaFuncSetAttribute(pair kernel): ") + cudaGetErrorString(e);
     return -2;
@@ -999,12 +1039,14 @@ inline int bind_weights(State* st, TcState* tc, const void* arena, int L) {
   return 0;
 }
 
-// One fused middle layer (reads and writes e): l >= 1 for TSP, any layer with write_e for MIS except layer 0.
+// One fused layer that writes e.  LUT mode (cl != nullptr): layer 0, whose input rows are one of two table rows (categorical
+// TSP: lut_x selects per edge; MIS: lut_x == nullptr, both tables zero) - GEMM1 and the input stream are replaced by lookups.
 // gn_part != nullptr (last layer of the sparse TSP encoder): the kernel also leaves the head's GroupNorm partial sums,
 // *gn_blocks = number of [32][2] blocks written.
 inline int launch(State* st, TcState* tc, int l, float* e, const float* uvab, float* partials, GraphDev g, LayerParams lp,
                   const float* tvec_edge, int agg_mode, cudaStream_t stream, double* gn_part = nullptr,
-                  int* gn_blocks = nullptr) {
+                  int* gn_blocks = nullptr, const float* lut_x = nullptr, const float* cl = nullptr,
+                  const float* lut = nullptr) {
   tc->last_launches = 0;
   if (!st->ready) {
     tc->err = "pair kernel: weights not bound";
@@ -1016,22 +1058,29 @@ inline int launch(State* st, TcState* tc, int l, float* e, const float* uvab, fl
   P.e = e; P.uvab = uvab; P.partials = partials; P.g = g; P.lp = lp; P.tvec = tvec_edge;
   P.zero_row = tc->zero_row4; P.debug_acc = tc->debug_acc; P.error_flag = tc->error_flag; P.phase_cycles = tc->phase_cycles;
   P.agg_mode = agg_mode; P.w_row_base = l * 12 * H;
-  P.gn_part = tc->debug_acc ? nullptr : gn_part; P.E = g.E;
+  P.gn_part = (tc->debug_acc || cl) ? nullptr : gn_part; P.E = g.E;
+  P.lut_x = lut_x; P.cl = cl; P.lut = lut;
   P.n_tiles = (g.E + TC_TILE - 1) / TC_TILE;
   P.probe = tc->probe;
   const int n_pairs = (P.n_tiles + 1) / 2;
   const int clusters = n_pairs < st->max_clusters ? n_pairs : st->max_clusters;
-  const bool gn = P.gn_part != nullptr;
-  if (agg_mode == AGG_MAX && gn) k_edge_layer_pair<true, true><<<2 * clusters, THREADS, SMEM_BYTES, stream>>>(st->wmap, tc->emap, P);
-  else if (agg_mode == AGG_MAX) k_edge_layer_pair<true, false><<<2 * clusters, THREADS, SMEM_BYTES, stream>>>(st->wmap, tc->emap, P);
-  else if (gn) k_edge_layer_pair<false, true><<<2 * clusters, THREADS, SMEM_BYTES, stream>>>(st->wmap, tc->emap, P);
-  else k_edge_layer_pair<false, false><<<2 * clusters, THREADS, SMEM_BYTES, stream>>>(st->wmap, tc->emap, P);
+  const int mode = cl ? MODE_LUT : (P.gn_part ? MODE_GN : MODE_PLAIN);
+  const int grid = 2 * clusters;
+  if (agg_mode == AGG_MAX) {
+    if (mode == MODE_LUT) k_edge_layer_pair<true, MODE_LUT><<<grid, THREADS, SMEM_BYTES, stream>>>(st->wmap, tc->emap, P);
+    else if (mode == MODE_GN) k_edge_layer_pair<true, MODE_GN><<<grid, THREADS, SMEM_BYTES, stream>>>(st->wmap, tc->emap, P);
+    else k_edge_layer_pair<true, MODE_PLAIN><<<grid, THREADS, SMEM_BYTES, stream>>>(st->wmap, tc->emap, P);
+  } else {
+    if (mode == MODE_LUT) k_edge_layer_pair<false, MODE_LUT><<<grid, THREADS, SMEM_BYTES, stream>>>(st->wmap, tc->emap, P);
+    else if (mode == MODE_GN) k_edge_layer_pair<false, MODE_GN><<<grid, THREADS, SMEM_BYTES, stream>>>(st->wmap, tc->emap, P);
+    else k_edge_layer_pair<false, MODE_PLAIN><<<grid, THREADS, SMEM_BYTES, stream>>>(st->wmap, tc->emap, P);
+  }
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) {
     tc->err = std::string("pair kernel launch: ") + cudaGetErrorString(err);
     return -2;
   }
-  if (gn_blocks) *gn_blocks = 2 * clusters * 4;
+  if (gn_blocks) *gn_blocks = P.gn_part ? 2 * clusters * 4 : 0;
   tc->last_launches = 1;
   return 0;
 }
