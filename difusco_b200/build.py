@@ -35,12 +35,12 @@ def needs_build():
   return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
 
 
-def build(force=False, verbose=False, prof=False, out=None):
+def build(force=False, verbose=False, prof=False, out=None, defines=()):
   """prof=True compiles the per-phase clock64 counters into the tcgen05 kernel (tuning only: they cost ~32
   registers per thread; scripts/probe_tc.py with DFB_TC_PROBE=128 reads them)."""
-  if not force and not prof and not needs_build():
+  if not force and not prof and not defines and not needs_build():
     return LIB
-  cmd = ([_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + (["-DDFB_PHASE_PROF"] if prof else []) +
+  cmd = ([_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + (["-DDFB_PHASE_PROF"] if prof else []) + list(defines) +
          ["-o", out or LIB] + SOURCES)
   r = subprocess.run(cmd, cwd=CSRC, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
   if r.returncode != 0:
@@ -52,4 +52,5 @@ def build(force=False, verbose=False, prof=False, out=None):
 
 if __name__ == "__main__":
   _out = sys.argv[sys.argv.index("--out") + 1] if "--out" in sys.argv else None
-  print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, prof="--prof" in sys.argv, out=_out))
+  print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, prof="--prof" in sys.argv, out=_out,
+              defines=[a for a in sys.argv[1:] if a.startswith("-D")]))   # tuning variants, e.g. -DDFB_WAIT_HINT_NS=0u

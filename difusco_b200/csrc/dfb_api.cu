@@ -1071,6 +1071,16 @@ extern "C" int dfb_debug_phase_cycles(dfb_ctx* ctx, unsigned long long* out) {
   return DFB_OK;
 }
 
+#ifdef DFB_PHASE_PROF
+// Tuning build only (not part of the ABI): time line of cluster 0's leader CTA, see g_pair_trace in edge_layer_v2.cuh.  out[512].
+extern "C" int dfb_debug_pair_trace(long long* out) {
+  if (!out) return DFB_E_INVALID;
+  if (cudaDeviceSynchronize() != cudaSuccess) return DFB_E_CUDA;
+  if (cudaMemcpyFromSymbol(out, dfb::v2::g_pair_trace, sizeof(long long) * 512) != cudaSuccess) return DFB_E_CUDA;
+  return DFB_OK;
+}
+#endif
+
 // Diagnostic: watchdog record of the tcgen05 kernel (host-mapped, readable even after a launch failure):
 // out[0] = wait-site code (0 = none), out[1] = blockIdx.x, out[2] = parity waited for, out[3] = threadIdx.x.
 extern "C" int dfb_debug_watchdog(dfb_ctx* ctx, int* out) {

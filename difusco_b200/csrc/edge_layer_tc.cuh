@@ -90,6 +90,9 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+#ifndef DFB_WAIT_HINT_NS
+#define DFB_WAIT_HINT_NS 20000u
+#endif
 // Bounded wait: a protocol bug must surface as a launch failure, not as a hung GPU.  try_wait suspends
 // the thread in hardware (up to the hint, in ns) instead of burning issue slots.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* error_flag, int code) {
@@ -100,7 +103,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* e
     asm volatile(
         "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}"
         : "=r"(ok)
-        : "r"(addr), "r"(parity), "r"(20000u)
+        : "r"(addr), "r"(parity), "r"(DFB_WAIT_HINT_NS)
         : "memory");
     if (ok) return;
     if (spin > 400000u) {   // >> any legitimate wait (each failed try_wait already slept up to 20 us)

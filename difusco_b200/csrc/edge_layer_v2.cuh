@@ -31,7 +31,11 @@
 namespace dfb {
 namespace v2 {
 
-constexpr int NA = 5, NB = 4;
+#ifndef DFB_NA
+#define DFB_NA 5
+#define DFB_NB 4
+#endif
+constexpr int NA = DFB_NA, NB = DFB_NB;   // ring depths; NA + NB = 9 stages of 16 KB (tuning: -DDFB_NA=6 -DDFB_NB=3 measured no faster)
 constexpr int STAGE = 16384;                       // one fp32 box [128 rows x 32 cols] == bf16 hi (8 KB) | lo (8 KB)
 constexpr int HALF = 8192;
 constexpr int NWORKW = 16;                         // worker warps
@@ -103,6 +107,9 @@ __device__ __forceinline__ void cluster_sync_all() {
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_MASK) : "memory");
 }
+#ifndef DFB_WAIT_HINT_NS
+#define DFB_WAIT_HINT_NS 20000u
+#endif
 // bounded wait on a barrier that the peer CTA also arrives on
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity, int* error_flag, int code) {
   const uint32_t addr = smem_u32(bar);
@@ -112,7 +119,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
     asm volatile(
         "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}"
         : "=r"(ok)
-        : "r"(addr), "r"(parity), "r"(20000u)
+        : "r"(addr), "r"(parity), "r"(DFB_WAIT_HINT_NS)
         : "memory");
     if (ok) return;
     if (spin > 400000u) {
@@ -214,6 +221,15 @@ __device__ __forceinline__ uint32_t sw64_off(int r, int j) {
 // GNSTATS: the last layer of the sparse TSP encoder also leaves the head's GroupNorm partial sums (own instantiation: the
 // extra live values would otherwise cost the other eleven layers registers in the X phase).
 enum { MODE_PLAIN = 0, MODE_GN = 1, MODE_LUT = 2 };
+#ifdef DFB_PHASE_PROF
+// Tuning build only: clock64 time line of cluster 0's leader CTA for tiles 3..6 (slot = (it - 3) * 128 + actor * 16 + event;
+// actors 0..3 = worker warp wq 0 of part 0..3, 4 = MMA thread, 5 = box loads, 6 = stores), layer 5 only.  scripts/probe_tc.py prints it.
+__device__ long long g_pair_trace[4 * 128];
+#define TRACE(actor, ev, it_) do { if ((P.probe & 128) && blockIdx.x == 0 && P.w_row_base == 5 * 12 * H && (it_) >= 3 && (it_) < 7) \
+    g_pair_trace[((it_) - 3) * 128 + (actor) * 16 + (ev)] = clock64(); } while (0)
+#else
+#define TRACE(actor, ev, it_) do { } while (0)
+#endif
 template <bool MAXAGG, int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap emap, const Params P) {
@@ -324,11 +340,12 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
           mbar_wait_cluster(&a_full[sa], (ga / NA) & 1, P.error_flag, 3);
           MMA_T1(wa);
           tc_fence_after();
-          const uint32_t a_hi = smem_base + OFF_A + sa * STAGE, a_lo = a_hi + HALF;
+          TRACE(4, kc, it);
+          const uint32_t a_hi = smem_base + OFF_A + sa * STAGE, a_lo = a_hi + 64;   // hi | lo halves of each 128-byte row
           const uint32_t b_hi = smem_base + OFF_B + sb * STAGE, b_lo = b_hi + HALF;
 #pragma unroll
           for (int ks = 0; ks < 2; ++ks) {
-            const uint64_t dah = umma_desc_sw64(a_hi + ks * 32), dal = umma_desc_sw64(a_lo + ks * 32);
+            const uint64_t dah = umma_desc_sw128(a_hi + ks * 32), dal = umma_desc_sw128(a_lo + ks * 32);
             const uint64_t dbh = umma_desc_sw64(b_hi + ks * 32), dbl = umma_desc_sw64(b_lo + ks * 32);
             umma2_bf16(tmem_base, dah, dbh, (kc | ks) ? 1u : 0u);
             umma2_bf16(tmem_base, dal, dbh, 1u);
@@ -346,6 +363,7 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
           MMA_T0();
           if ((kc & 1) == 0) mbar_wait_cluster(&a2_full[kc >> 1], it & 1, P.error_flag, 13);
           MMA_T1(w2);
+          if ((kc & 1) == 0) TRACE(4, 8 + (kc >> 1), it);
           MMA_T0();
           mbar_wait(&b_full[sb], (ub / NB) & 1, P.error_flag, 12);
           MMA_T1(wb);
@@ -362,6 +380,7 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
           umma2_commit(&b_empty[sb]);
         }
         umma2_commit(&acc_rdy[1]);
+        TRACE(4, 12, it);
       }
 #ifdef DFB_PHASE_PROF
       if (P.probe & 128) {   // MMA thread's waits: [21] A stages (GEMM1), [22] weights, [23] GEMM2 A chunks; per tile PAIR
@@ -409,6 +428,7 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
           const uint32_t sa = ga % NA;
           mbar_wait(&a_empty[sa], ((ga / NA) & 1) ^ 1, P.error_flag, 4);
           mbar_arrive_expect_tx(&box_full[b], STAGE);
+          TRACE(5, b, it);
           tma_load_2d_hint(smem_base + OFF_A + sa * STAGE, &emap, &box_full[b], 32 * b, tile * TC_TILE, pol_stream);
         }
       }
@@ -427,6 +447,7 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
             mbar_wait(&out_full[p2], j, P.error_flag, 8);   // two phases per tile: parity == j
             tma_store_2d_hint(&emap, smem_base + OFF_G + p2 * PART_G, 32 * (p2 + 4 * j), tile_of(it) * TC_TILE, pol_stream);
             tma_store_commit();
+            TRACE(6, 4 * j + p2, it);
             if (pending >= 0) {          // the store before this one has been read once at most one group is pending
               tma_store_wait_read_n<1>();
               mbar_arrive(&stage_free[pending]);
@@ -454,14 +475,6 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
     const uint32_t t_acc1 = tmem_base + ((uint32_t)(wq * 32) << 16);
     const uint32_t t_acc2 = t_acc1 + 256u;
     auto worker_bar = [] { asm volatile("bar.sync 1, %0;" ::"n"(NWORK) : "memory"); };
-    auto part_bar = [&] {   // the four warps of this part; immediate barrier ids (tools such as racecheck model those)
-      switch (part) {
-        case 0: asm volatile("bar.sync 2, 128;" ::: "memory"); break;
-        case 1: asm volatile("bar.sync 3, 128;" ::: "memory"); break;
-        case 2: asm volatile("bar.sync 4, 128;" ::: "memory"); break;
-        default: asm volatile("bar.sync 5, 128;" ::: "memory"); break;
-      }
-    };
     auto stat_buf = [&](int p2) { return reinterpret_cast<float*>(smem + OFF_G + (p2 * 4 + wq) * 2 * GBUF); };
 #ifdef DFB_PHASE_PROF
     const bool prof = (P.probe & 128) && ww == 0 && lane == 0;
@@ -473,6 +486,11 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
 #define XSUB(i) do { } while (0)
 #endif
     uint32_t gbox = 0;   // global input-box counter of this CTA (operand ring position)
+#ifdef DFB_PHASE_PROF
+#define WTR(ev) do { if (wq == 0 && lane == 0) TRACE(part, ev, it); } while (0)
+#else
+#define WTR(ev) do { } while (0)
+#endif
     const uint64_t pol_keep = l2_policy_evict_last();
     bool prev_valid = false;   // this thread's row of the previous tile is a real edge (GroupNorm statistics)
     for (int it = 0; it <= n_my; ++it) {
@@ -481,122 +499,141 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
 #ifdef DFB_PHASE_PROF
       if (prof) tp = clock64();
 #endif
-      worker_bar();   // every warp has left E3 of the previous tile: the gather buffers (LayerNorm exchange) are free
+      // No barrier here: the first write into the gather buffers / staging of this iteration (E4 of the previous tile) waits
+      // for GEMM2, whose last K-chunk needs every worker warp's arrival after its last read of the LayerNorm exchange
 
       // ================= X phase: this part's two boxes (part, part + 4): convert tile `it`, finish tile `it - 1` =========
 #ifdef DFB_PHASE_PROF
       if (prof) tx = clock64();
 #endif
+      WTR(0);
       int xsel = 0;   // LUT mode: table row of this thread's edge
       if (LUT && have_tile) {
         mbar_wait(&idx_full[it & 1], (it >> 1) & 1, P.error_flag, 22);
         const int cv = (reinterpret_cast<const int*>(smem + OFF_IDX) + (it & 1) * IDX_INTS + TC_TILE)[r];
         xsel = (cv >= 0) ? ((cv >> 30) & 1) : 0;
       }
-      for (int j = 0; j < 2; ++j) {
+      // Per box: convert (GEMM2's tail of the previous tile drains meanwhile), copy the previous tile's result box out (E4),
+      // preload the residual (the box's fp32 values stay in registers across the E4).  Tried and slower: E4 of box `part`
+      // first (the workers then idle for the whole GEMM2 tail, ~3.5k cycles including the barrier wake-ups).
+      auto load_lut = [&](int b, float4 (&xin)[8]) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) xin[q] = __ldg(reinterpret_cast<const float4*>(P.lut + xsel * H + 32 * b) + q);
+      };
+      auto convert_box = [&](int j, float4 (&xin)[8]) {
         const int b = part + 4 * j;
-        float4 xin[8];
-        if (LUT && have_tile) {
+        const uint32_t g = gbox + b, sa = g % NA;
+        mbar_wait(&box_full[b], it & 1, P.error_flag, 5);
+        XSUB(0);   // wait for the input box
+        WTR(1 + 5 * j);
+        unsigned char* stage = smem + OFF_A + sa * STAGE;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) xin[q] = __ldg(reinterpret_cast<const float4*>(P.lut + xsel * H + 32 * b) + q);
+        for (int q = 0; q < 8; ++q) xin[q] = *reinterpret_cast<const float4*>(stage + sw128_off(r, q));
+        // in place and row-local: the A operand is ONE 128B-swizzled K-major tile whose 64 bf16 per row are the box's
+        // 32 hi values followed by its 32 lo values, so a row's 128 operand bytes replace exactly its own 128 fp32 bytes
+        // (same swizzle as the TMA box) - no other thread's row is touched, no barrier (the fp32 values stay live in
+        // registers: they are also the residual preloaded below)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint2 h0, l0, h1, l1;
+          split4(xin[2 * q], h0, l0);
+          split4(xin[2 * q + 1], h1, l1);
+          *reinterpret_cast<uint4*>(stage + sw128_off(r, q)) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+          *reinterpret_cast<uint4*>(stage + sw128_off(r, 4 + q)) = make_uint4(l0.x, l0.y, l1.x, l1.y);
         }
-        if (!LUT && have_tile) {
-          const uint32_t g = gbox + b, sa = g % NA;
-          mbar_wait(&box_full[b], it & 1, P.error_flag, 5);
-          XSUB(0);   // wait for the input box
-          unsigned char* stage = smem + OFF_A + sa * STAGE;
+        fence_proxy_async();
+        tc_fence_before();   // orders this thread's earlier TMEM accesses (previous tile) before the MMA overwrites acc1
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(&a_full[sa]);
+        XSUB(1);   // conversion
+        WTR(2 + 5 * j);
+      };
+      auto e4_box = [&](int j) {
+        // E4 of the previous tile for box b: acc2 already holds e_in + b_O + s O^T (the residual was preloaded)
+        const int b = part + 4 * j;
+        if (j == 0) {
+          mbar_wait(&acc_rdy[1], (it - 1) & 1, P.error_flag, 7);
+          tc_fence_after();
+        } else {
+          mbar_wait(&stage_free[part], 0, P.error_flag, 10);   // the store of box `part` has read the staging
+        }
+        XSUB(2);   // wait for GEMM2 / the staging
+        WTR(3 + 5 * j);
+        float gs[8];   // last layer: this row's sums / sums of squares of the 4 GroupNorm groups (8 channels each) of the box
 #pragma unroll
-          for (int q = 0; q < 8; ++q) xin[q] = *reinterpret_cast<const float4*>(stage + sw128_off(r, q));
-          // in place: all 128 rows of the box have been read before any bf16 row is written over them (only the fp32
-          // values stay live across the barrier; they are also the residual preloaded below)
-          part_bar();
+        for (int g2 = 0; g2 < 4; ++g2) {   // 8 columns == one GroupNorm group at a time: few live registers next to xin
+          uint32_t v[8];
+          tmem_ld8(t_acc2 + 32 * b + 8 * g2, v);
+          tmem_wait_ld();
+          *reinterpret_cast<float4*>(stagebox + sw128_off(r, 2 * g2)) =
+              make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
+          *reinterpret_cast<float4*>(stagebox + sw128_off(r, 2 * g2 + 1)) =
+              make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7]));
+          if (GNSTATS) {
+            float sv = 0.f, qv = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float xv = __uint_as_float(v[i]);
+              sv += xv;
+              qv = fmaf(xv, xv, qv);
+            }
+            gs[2 * g2] = prev_valid ? sv : 0.f;
+            gs[2 * g2 + 1] = prev_valid ? qv : 0.f;
+          }
+        }
+        if (GNSTATS) {
+          // 8 values x 32 rows -> lane k (k < 8) holds the warp total of value k (butterfly transpose-reduce: 9 shuffles),
+          // accumulated in fp64 per warp: the statistics span all E edges of the call (gnn_encoder.py:400, batch dim 1)
+#pragma unroll
+          for (int off = 4; off >= 1; off >>= 1) {
+            const bool up = (lane & off) != 0;
+#pragma unroll
+            for (int i = 0; i < off; ++i) {
+              const float send = up ? gs[i] : gs[i + off], keep = up ? gs[i + off] : gs[i];
+              gs[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+            }
+          }
+          float tot = gs[0];
+          tot += __shfl_xor_sync(0xffffffffu, tot, 8);
+          tot += __shfl_xor_sync(0xffffffffu, tot, 16);
+          // lane L holds the warp total of value index L & 7 (= 2 * group + {sum, sum of squares})
+          if (lane < 8) reinterpret_cast<double*>(smem + OFF_GN)[ww * 16 + j * 8 + lane] += (double)tot;
+        }
+        fence_proxy_async();   // generic-proxy writes -> visible to the TMA store
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&out_full[part]);
+        XSUB(3);   // E4 copy-out
+        WTR(4 + 5 * j);
+      };
+      auto preload_box = [&](int j, const float4 (&xin)[8]) {
+        // preload GEMM2's accumulator with the residual: acc2[:, box b] = e_in + b_O (this thread's own lane; E4 of the
+        // previous tile has read these columns)
+        const int b = part + 4 * j;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t v[16];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            uint2 h0, l0, h1, l1;
-            split4(xin[2 * q], h0, l0);
-            split4(xin[2 * q + 1], h1, l1);
-            *reinterpret_cast<uint4*>(stage + sw64_off(r, q)) = make_uint4(h0.x, h0.y, h1.x, h1.y);
-            *reinterpret_cast<uint4*>(stage + HALF + sw64_off(r, q)) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+            const float4 bo = *reinterpret_cast<const float4*>(prm + 5 * H + 32 * b + 16 * hh + 4 * q);
+            const float4 xx = xin[4 * hh + q];
+            const float2 o0 = add2(make_float2(xx.x, xx.y), make_float2(bo.x, bo.y));
+            const float2 o1 = add2(make_float2(xx.z, xx.w), make_float2(bo.z, bo.w));
+            v[4 * q] = __float_as_uint(o0.x); v[4 * q + 1] = __float_as_uint(o0.y);
+            v[4 * q + 2] = __float_as_uint(o1.x); v[4 * q + 3] = __float_as_uint(o1.y);
           }
-          fence_proxy_async();
-          tc_fence_before();   // orders this thread's earlier TMEM accesses (previous tile) before the MMA overwrites acc1
-          __syncwarp();
-          if (lane == 0) mbar_arrive_leader(&a_full[sa]);
-          XSUB(1);   // conversion
+          tmem_st16(t_acc2 + 32 * b + 16 * hh, v);
         }
-        if (it > 0 && !debug) {
-          // E4 of the previous tile for box b: acc2 already holds e_in + b_O + s O^T (the residual was preloaded)
-          if (j == 0) {
-            mbar_wait(&acc_rdy[1], (it - 1) & 1, P.error_flag, 7);
-            tc_fence_after();
-          } else {
-            mbar_wait(&stage_free[part], 0, P.error_flag, 10);   // the store of box `part` has read the staging
-          }
-          XSUB(2);   // wait for GEMM2 / the staging
-          float gs[8];   // last layer: this row's sums / sums of squares of the 4 GroupNorm groups (8 channels each) of the box
-#pragma unroll
-          for (int g2 = 0; g2 < 4; ++g2) {   // 8 columns == one GroupNorm group at a time: few live registers next to xin
-            uint32_t v[8];
-            tmem_ld8(t_acc2 + 32 * b + 8 * g2, v);
-            tmem_wait_ld();
-            *reinterpret_cast<float4*>(stagebox + sw128_off(r, 2 * g2)) =
-                make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
-            *reinterpret_cast<float4*>(stagebox + sw128_off(r, 2 * g2 + 1)) =
-                make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7]));
-            if (GNSTATS) {
-              float sv = 0.f, qv = 0.f;
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float xv = __uint_as_float(v[i]);
-                sv += xv;
-                qv = fmaf(xv, xv, qv);
-              }
-              gs[2 * g2] = prev_valid ? sv : 0.f;
-              gs[2 * g2 + 1] = prev_valid ? qv : 0.f;
-            }
-          }
-          if (GNSTATS) {
-            // 8 values x 32 rows -> lane k (k < 8) holds the warp total of value k (butterfly transpose-reduce: 9 shuffles),
-            // accumulated in fp64 per warp: the statistics span all E edges of the call (gnn_encoder.py:400, batch dim 1)
-#pragma unroll
-            for (int off = 4; off >= 1; off >>= 1) {
-              const bool up = (lane & off) != 0;
-#pragma unroll
-              for (int i = 0; i < off; ++i) {
-                const float send = up ? gs[i] : gs[i + off], keep = up ? gs[i + off] : gs[i];
-                gs[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-              }
-            }
-            float tot = gs[0];
-            tot += __shfl_xor_sync(0xffffffffu, tot, 8);
-            tot += __shfl_xor_sync(0xffffffffu, tot, 16);
-            // lane L holds the warp total of value index L & 7 (= 2 * group + {sum, sum of squares})
-            if (lane < 8) reinterpret_cast<double*>(smem + OFF_GN)[ww * 16 + j * 8 + lane] += (double)tot;
-          }
-          fence_proxy_async();   // generic-proxy writes -> visible to the TMA store
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&out_full[part]);
-          XSUB(3);   // E4 copy-out
+        XSUB(4);   // residual preload
+        WTR(5 + 5 * j);
+      };
+      const bool finish_prev = it > 0 && !debug;
+      for (int j = 0; j < 2; ++j) {
+        float4 xin[8];
+        if (have_tile) {
+          if (LUT) load_lut(part + 4 * j, xin); else convert_box(j, xin);
         }
-        if (have_tile && !debug) {
-          // preload GEMM2's accumulator with the residual: acc2[:, box b] = e_in + b_O (this thread's own lane; it read
-          // these columns for E4 just above)
-#pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            uint32_t v[16];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float4 bo = *reinterpret_cast<const float4*>(prm + 5 * H + 32 * b + 16 * hh + 4 * q);
-              const float4 xx = xin[4 * hh + q];
-              const float2 o0 = add2(make_float2(xx.x, xx.y), make_float2(bo.x, bo.y));
-              const float2 o1 = add2(make_float2(xx.z, xx.w), make_float2(bo.z, bo.w));
-              v[4 * q] = __float_as_uint(o0.x); v[4 * q + 1] = __float_as_uint(o0.y);
-              v[4 * q + 2] = __float_as_uint(o1.x); v[4 * q + 3] = __float_as_uint(o1.y);
-            }
-            tmem_st16(t_acc2 + 32 * b + 16 * hh, v);
-          }
-          XSUB(4);   // residual preload
-        }
+        if (finish_prev) e4_box(j);
+        if (have_tile && !debug) preload_box(j, xin);
       }
       gbox += 8;
       if (!have_tile) break;
@@ -664,6 +701,7 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
         cp_async_commit();
       };
       XSUB(5);   // endpoints, segments, gather pointers
+      WTR(11);
       if (!debug) {
         if (it > 0) mbar_wait(&stage_free[part], 1, P.error_flag, 11);   // the store of box part + 4 has read the staging
         XSUB(6);   // wait for the staging before the first gathers
@@ -671,6 +709,7 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
         gather_issue(1, gbuf0 + GBUF);
       }
       PHASE(0);   // X phase
+      WTR(12);
       const int s_edge = tile * TC_TILE + r;
       prev_valid = valid;
       if (!LUT) {
@@ -678,6 +717,7 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
         tc_fence_after();
       }
       PHASE(1);   // wait for GEMM1
+      WTR(13);
       if (debug) {
 #pragma unroll 1
         for (int c0 = cbase; c0 < cbase + 64; c0 += 32) {
@@ -877,6 +917,7 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
         rstd1 = rsqrtf(fmaxf(ss * (1.0f / H), 0.0f) + LN_EPS);
       }
       PHASE(2);   // E1
+      WTR(14);
       // ================= E2: e_til = relu(LN_e(e_hat)) + tau, statistics for LN_O =================
       float S2, Q2;
       {
@@ -968,6 +1009,7 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
         if (lane == 0) mbar_arrive_leader(&a2_full[kc]);
       }
       PHASE(4);   // E3
+      WTR(15);
     }
     if (GNSTATS && lane < 8) {
       // block = (CTA, lane quarter) supplies all 32 groups: warp (part, wq) owns groups 4 (part + 4 j) + g
@@ -987,6 +1029,7 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
 #endif
 #undef PHASE
 #undef XSUB
+#undef WTR
   }
 
   // teardown: nobody may leave while the peer can still signal this CTA's barriers or read its shared memory

@@ -53,6 +53,21 @@ def t_forward(tag):
       nlead = npair / 2   # tile pairs: the leader CTA's MMA thread
       print(f"{tag}: pair kernel MMA-thread waits per tile pair: A stages {pc[21] / nlead:.0f}  weights {pc[22] / nlead:.0f}  "
             f"GEMM2 A chunks {pc[23] / nlead:.0f}", flush=True)
+    L = _cabi.lib()
+    if hasattr(L, "dfb_debug_pair_trace"):   # --prof build: time line of cluster 0's leader CTA, tiles 3..6 (last launch)
+      import ctypes as C
+      buf = (C.c_longlong * 512)()
+      L.dfb_debug_pair_trace(buf)
+      tr = np.array(buf[:], dtype=np.int64).reshape(4, 8, 16)
+      t0 = tr[0, 0, 0]
+      wn = ["Xstart", "box0", "conv0", "G2/st0", "E4_0", "pre0", "box1", "conv1", "st1", "E4_1", "pre1", "setup", "gath", "G1", "E1", "E3"]
+      for itx in range(4):
+        for a in range(4):
+          print(f"{tag}: trace tile {itx + 3} part {a}: " + " ".join(f"{n}={tr[itx, a, k] - t0}" for k, n in enumerate(wn)), flush=True)
+        print(f"{tag}: trace tile {itx + 3} MMA: G1 chunks " + " ".join(str(tr[itx, 4, k] - t0) for k in range(8)) +
+              " | G2 chunks " + " ".join(str(tr[itx, 4, 8 + k] - t0) for k in range(4)) + f" | end {tr[itx, 4, 12] - t0}", flush=True)
+        print(f"{tag}: trace tile {itx + 3} box loads: " + " ".join(str(tr[itx, 5, k] - t0) for k in range(8)) +
+              " | stores: " + " ".join(str(tr[itx, 6, k] - t0) for k in range(8)), flush=True)
     sub = ["tmemwait", "gatherwait", "math", "gissue", "reduce"]
     print(f"{tag}: E1 sub-phases cycles/tile " + " ".join(f"{n}={c / ntile_cta:.0f}" for n, c in zip(sub, pc[8:13])), flush=True)
 
