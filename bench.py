@@ -473,8 +473,9 @@ def run_ours(args, rank, world, local_rank):
                          "scope": "whole denoise step: every launch of the timed loop (CUDA-graph replay), timed with CUDA "
                                   "events around the loop; algorithmic bytes = SURVEY 8(d) per step",
                          "algorithmic_bytes_per_step": step_bytes, "denoise_steps_timed": DENOISE_STEPS * args.steps,
-                         "kernel": {"name": "k_edge_layer_pair (CTA-pair fused edge layer; layer 0 and the MIS last layer: "
-                                            "k_edge_layer_tc16w)" if impl == "tc" else impl,
+                         "kernel": {"name": "k_edge_layer_pair (CTA-pair fused edge layer, all 12 layers; layer 0 in table-lookup "
+                                            "mode without the input read; the MIS last layer: k_edge_layer_tc16w)"
+                                    if impl == "tc" else impl,
                                     "algorithmic_bytes_per_launch": per_launch_bytes, "launches_timed": int(edge_n),
                                     "ms_per_launch": k_ms, "achieved": k_achieved, "frac": k_achieved / peak,
                                     "share_of_step": edge_ms / plain_ms if plain_ms > 0 else None,

@@ -89,6 +89,7 @@ struct dfb_ctx {
   TcState tc;
   v2::State pair;   // round-2 CTA-pair kernel (middle layers of the product path)
   bool pair_enabled = true;    // DFB_PAIR_KERNEL=0 routes every layer to the single-CTA kernel (A/B timing)
+  bool serpentine = true;      // DFB_SERPENTINE=0: every layer sweeps the edge stream upwards (A/B timing)
 };
 
 #define FAIL(ctx, code, ...)                         \
@@ -220,6 +221,8 @@ extern "C" int dfb_create(dfb_ctx** out, int device) {
   {
     const char* pk = getenv("DFB_PAIR_KERNEL");
     if (pk) ctx->pair_enabled = atoi(pk) != 0;
+    const char* sp = getenv("DFB_SERPENTINE");
+    if (sp) ctx->serpentine = atoi(sp) != 0;
   }
   r = v2::init(&ctx->pair, &ctx->tc);
   if (r != 0) {
@@ -710,9 +713,13 @@ static int launch_edge_layer(dfb_ctx* ctx, int l, const float* uvab, const float
     const bool lut_mode = e_zero || xt_for_lut;
     const float* cl = lut_mode ? (e_zero ? ctx->cl0 + 2 * H : ctx->cl0) : nullptr;       // e0 = 0: zero tables
     const float* lut = lut_mode ? (e_zero ? ctx->cl0 + 2 * H : ctx->lut) : nullptr;
+    // the last layer that writes e (TSP: L-1, read next by the head from row 0 up; MIS: L-2, read by the last layer's
+    // kernel from tile 0 up) sweeps the edge stream downwards, the one before it upwards, and so on
+    const int last_writer = ctx->node_only ? ctx->L - 2 : ctx->L - 1;
+    const int sweep_down = (((last_writer - l) & 1) == 0 && l <= last_writer && ctx->serpentine) ? 1 : 0;
     int r = v2::launch(&ctx->pair, &ctx->tc, l, (float*)ctx->e.p, uvab, (float*)ctx->partials.p, ctx->g, ctx->layers[l],
                        tvec_edge, ctx->agg_mode, st, gn_blocks ? (double*)ctx->gn_part.p : nullptr, gn_blocks,
-                       xt_for_lut, cl, lut);
+                       xt_for_lut, cl, lut, sweep_down);
     if (r) FAIL(ctx, DFB_E_CUDA, "tcgen05 pair edge layer: %s", ctx->tc.err.c_str());
     ctx->launches += ctx->tc.last_launches;
   } else {

@@ -58,7 +58,8 @@ constexpr int SMEM_BYTES = OFF_BAR + 52 * 8;
 static_assert(NA <= 6 && NB <= 6, "barrier slots");
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 static_assert(GBUF % 128 == 0, "gather buffers stay 128-byte aligned");
-static_assert(PART_G >= STAGE && PART_G % 1024 == 0 && OFF_G % 1024 == 0, "a part's gather buffers hold one 128B-swizzled fp32 box");
+static_assert(OFF_G % 1024 == 0 && (2 * GBUF) % 512 == 0 && 2 * GBUF >= 4096 + 512,
+              "every worker warp's gather buffers contain a 1024-byte aligned 4 KB window (its E4 staging, 128B swizzle)");
 
 // UMMA instruction descriptor: D=F32, A=B=BF16, K-major, N=256, M=256 (the pair), cute::UMMA::InstrDescriptor
 constexpr uint32_t IDESC2 = (1u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((256u >> 4) << 24);
@@ -86,6 +87,7 @@ struct Params {
   int w_row_base;         // row of this layer's C_hi block in the bf16 weight arena
   int n_tiles;
   int probe;
+  int reverse;            // sweep the tile pairs from the end of the edge stream to its start
 };
 
 // ----------------------------------------------------------------------------------------------
@@ -109,6 +111,9 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
 }
 #ifndef DFB_WAIT_HINT_NS
 #define DFB_WAIT_HINT_NS 20000u
+#endif
+#ifndef DFB_EXP
+#define DFB_EXP 0   // timing experiments (results wrong): 2 = no result stores, 4 = stores never awaited, 8 = every CTA stores to its own first tile (L2-resident)
 #endif
 // bounded wait on a barrier that the peer CTA also arrives on
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity, int* error_flag, int code) {
@@ -232,7 +237,8 @@ __device__ long long g_pair_trace[4 * 128];
 #endif
 template <bool MAXAGG, int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
-k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap emap, const Params P) {
+k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap emap,
+                  const __grid_constant__ CUtensorMap smap, const Params P) {
   constexpr bool GNSTATS = MODE == MODE_GN;
   constexpr bool LUT = MODE == MODE_LUT;   // no GEMM1, no input boxes: acc1 and the residual come from two-row tables
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -248,8 +254,7 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
   uint64_t* b_empty = bars + 26;    // [NB] MMA commit (multicast)
   uint64_t* acc_rdy = bars + 32;    // [2]  MMA commit (multicast): GEMM1 / GEMM2 accumulator complete
   uint64_t* a2_full = bars + 34;    // [4]  LEADER: GEMM2 A chunk (64 columns of s) written to TMEM by both CTAs
-  uint64_t* out_full = bars + 38;   // [4]  part p wrote a result box into its staging (4 warps)
-  uint64_t* stage_free = bars + 42; // [4]  the TMA store has read part p's staging (I/O warp)
+  // bars + 38 .. 45: unused (the result stores are issued and awaited by the worker warps themselves)
   uint64_t* idx_full = bars + 46;   // [2]  edge endpoints of a tile in shared memory (32 lanes of warp 2)
   uint64_t* idx_free = bars + 48;   // [2]  the 16 worker warps are done with them
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 50);
@@ -262,7 +267,13 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
   const int n_my = (cid < n_pairs) ? (n_pairs - cid + n_clusters - 1) / n_clusters : 0;
   const bool debug = P.debug_acc != nullptr;
   const uint32_t smem_base = smem_u32(smem);
-  auto tile_of = [&](int it) { return 2 * (cid + it * n_clusters) + (int)rank; };
+  // tile pairs in ascending order, or descending when P.reverse: consecutive layers sweep the edge stream in opposite
+  // directions, so a layer starts on the rows the previous one wrote last (partly still in L2: -8 % DRAM traffic on every
+  // second layer, ncu --cache-control none; storing the tail of a sweep without the evict_first hint changed nothing)
+  auto tile_of = [&](int it) {
+    const int q = cid + it * n_clusters;
+    return 2 * (P.reverse ? n_pairs - 1 - q : q) + (int)rank;
+  };
 
   if (threadIdx.x == 0) {
     if (smem_base & 1023u) {   // the operand swizzles assume a 1024-byte aligned base
@@ -273,7 +284,7 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
     for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], 8); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     mbar_init(&acc_rdy[0], 1); mbar_init(&acc_rdy[1], 1);
-    for (int i = 0; i < 4; ++i) { mbar_init(&a2_full[i], 2 * NWORKW); mbar_init(&out_full[i], 4); mbar_init(&stage_free[i], 1); }
+    for (int i = 0; i < 4; ++i) mbar_init(&a2_full[i], 2 * NWORKW);
     for (int i = 0; i < 2; ++i) { mbar_init(&idx_full[i], 32); mbar_init(&idx_free[i], NWORKW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_proxy_async();
@@ -435,34 +446,8 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
       __syncwarp();
     }
   } else if (warp == 3) {
-    // ===================================== result boxes out =====================================
-    // part p stages box p, then box p + 4 of a tile in its own gather buffers; the store is issued here and the part is told
-    // when the staging has been read
-    if (lane == 0 && !debug) {
-      const uint64_t pol_stream = l2_policy_evict_first();
-      int pending = -1;   // part whose store was issued last and whose staging has not been released yet
-      for (int it = 0; it < n_my; ++it) {
-        for (int j = 0; j < 2; ++j) {
-          for (int p2 = 0; p2 < 4; ++p2) {
-            mbar_wait(&out_full[p2], j, P.error_flag, 8);   // two phases per tile: parity == j
-            tma_store_2d_hint(&emap, smem_base + OFF_G + p2 * PART_G, 32 * (p2 + 4 * j), tile_of(it) * TC_TILE, pol_stream);
-            tma_store_commit();
-            TRACE(6, 4 * j + p2, it);
-            if (pending >= 0) {          // the store before this one has been read once at most one group is pending
-              tma_store_wait_read_n<1>();
-              mbar_arrive(&stage_free[pending]);
-            }
-            pending = p2;
-            if (j == 1 && p2 == 3) {     // last store of the tile: the gathers of the next E1 wait for it
-              tma_store_wait_read_n<0>();
-              mbar_arrive(&stage_free[pending]);
-              pending = -1;
-            }
-          }
-        }
-      }
-      tma_store_wait_all();
-    }
+    // (no role: the workers issue their own result stores; the warp keeps the worker warps' ids congruent to their TMEM
+    //  lane quarter)
   } else {
     // ===================================== row workers =====================================
     const int wq = warp & 3;                 // TMEM lane quarter this warp may access (hardware rule: warp id % 4)
@@ -471,7 +456,12 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
     const int r = wq * 32 + lane;            // tile row == TMEM lane
     const int cbase = part * 64;
     unsigned char* gbuf0 = smem + OFF_G + ww * 2 * GBUF;
-    unsigned char* stagebox = smem + OFF_G + part * PART_G;   // this part's E4 staging: [128 rows][32 fp32], 128B swizzle
+    // E4 staging of this warp's 32 rows of a result box: [32 rows][32 fp32], 128B swizzle, inside the warp's own gather
+    // buffers (the first 1024-byte aligned window: the region starts at a multiple of 512).  The warp stores it itself
+    // (lane 0: TMA store + bulk group) and waits for its own bulk-group read before it reuses the window - no hop
+    // through another warp, no barrier shared with the other warps of the part.
+    unsigned char* stagewin = gbuf0 + ((1024u - (smem_u32(gbuf0) & 1023u)) & 1023u);
+    const uint64_t pol_stream = l2_policy_evict_first();
     const uint32_t t_acc1 = tmem_base + ((uint32_t)(wq * 32) << 16);
     const uint32_t t_acc2 = t_acc1 + 256u;
     auto worker_bar = [] { asm volatile("bar.sync 1, %0;" ::"n"(NWORK) : "memory"); };
@@ -555,7 +545,8 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
           mbar_wait(&acc_rdy[1], (it - 1) & 1, P.error_flag, 7);
           tc_fence_after();
         } else {
-          mbar_wait(&stage_free[part], 0, P.error_flag, 10);   // the store of box `part` has read the staging
+          if (lane == 0 && !(DFB_EXP & 4)) tma_store_wait_read_n<0>();   // this warp's store of box `part` has read the window
+          __syncwarp();
         }
         XSUB(2);   // wait for GEMM2 / the staging
         WTR(3 + 5 * j);
@@ -565,9 +556,9 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
           uint32_t v[8];
           tmem_ld8(t_acc2 + 32 * b + 8 * g2, v);
           tmem_wait_ld();
-          *reinterpret_cast<float4*>(stagebox + sw128_off(r, 2 * g2)) =
+          *reinterpret_cast<float4*>(stagewin + sw128_off(lane, 2 * g2)) =
               make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
-          *reinterpret_cast<float4*>(stagebox + sw128_off(r, 2 * g2 + 1)) =
+          *reinterpret_cast<float4*>(stagewin + sw128_off(lane, 2 * g2 + 1)) =
               make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7]));
           if (GNSTATS) {
             float sv = 0.f, qv = 0.f;
@@ -601,7 +592,11 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
         }
         fence_proxy_async();   // generic-proxy writes -> visible to the TMA store
         __syncwarp();
-        if (lane == 0) mbar_arrive(&out_full[part]);
+        if (lane == 0 && !(DFB_EXP & 2)) {
+          tma_store_2d_hint(&smap, smem_u32(stagewin), 32 * b,
+                            ((DFB_EXP & 8) ? (int)blockIdx.x : tile_of(it - 1)) * TC_TILE + wq * 32, pol_stream);
+          tma_store_commit();
+        }
         XSUB(3);   // E4 copy-out
         WTR(4 + 5 * j);
       };
@@ -703,7 +698,10 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
       XSUB(5);   // endpoints, segments, gather pointers
       WTR(11);
       if (!debug) {
-        if (it > 0) mbar_wait(&stage_free[part], 1, P.error_flag, 11);   // the store of box part + 4 has read the staging
+        if (it > 0) {   // this warp's store of box part + 4 has read the window: the gathers may overwrite it
+          if (lane == 0 && !(DFB_EXP & 4)) tma_store_wait_read_n<0>();
+          __syncwarp();
+        }
         XSUB(6);   // wait for the staging before the first gathers
         gather_issue(0, gbuf0);
         gather_issue(1, gbuf0 + GBUF);
@@ -1011,6 +1009,7 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
       PHASE(4);   // E3
       WTR(15);
     }
+    if (lane == 0) tma_store_wait_all();   // this warp's result stores
     if (GNSTATS && lane < 8) {
       // block = (CTA, lane quarter) supplies all 32 groups: warp (part, wq) owns groups 4 (part + 4 j) + g
       const double* acc = reinterpret_cast<const double*>(smem + OFF_GN) + ww * 16;
@@ -1048,6 +1047,9 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
 struct State {
   bool ready = false;
   CUtensorMap wmap;   // bf16 weight arena, box 32 K x 128 rows, 64B swizzle
+  CUtensorMap smap;   // fp32 edge stream, box 32 columns x 32 rows, 128B swizzle: one worker warp's rows of a result box
+  const void* smap_ptr = nullptr;
+  long long smap_rows = 0;
   int max_clusters = 0;
 };
 
@@ -1089,7 +1091,7 @@ inline int bind_weights(State* st, TcState* tc, const void* arena, int L) {
 inline int launch(State* st, TcState* tc, int l, float* e, const float* uvab, float* partials, GraphDev g, LayerParams lp,
                   const float* tvec_edge, int agg_mode, cudaStream_t stream, double* gn_part = nullptr,
                   int* gn_blocks = nullptr, const float* lut_x = nullptr, const float* cl = nullptr,
-                  const float* lut = nullptr) {
+                  const float* lut = nullptr, int reverse = 0) {
   tc->last_launches = 0;
   if (!st->ready) {
     tc->err = "pair kernel: weights not bound";
@@ -1097,6 +1099,24 @@ inline int launch(State* st, TcState* tc, int l, float* e, const float* uvab, fl
   }
   int r = tc_ensure_emap(tc, e, g.E);
   if (r) return r;
+  {
+    const long long e_rows = (long long)((g.E + TC_TILE - 1) / TC_TILE) * TC_TILE;
+    if (st->smap_ptr != (const void*)e || st->smap_rows != e_rows) {
+      cuuint64_t gdim[2] = {(cuuint64_t)H, (cuuint64_t)e_rows};
+      cuuint64_t gstride[1] = {(cuuint64_t)H * sizeof(float)};
+      cuuint32_t box[2] = {32u, 32u};
+      cuuint32_t estr[2] = {1u, 1u};
+      CUresult cr = ((PFN_encodeTiled)tc->encode_fn)(&st->smap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)e, gdim, gstride, box, estr,
+                                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (cr != CUDA_SUCCESS) {
+        tc->err = "cuTensorMapEncodeTiled(e, 32-row store box) failed with CUresult " + std::to_string((int)cr);
+        return -2;
+      }
+      st->smap_ptr = (const void*)e;
+      st->smap_rows = e_rows;
+    }
+  }
   Params P;
   P.e = e; P.uvab = uvab; P.partials = partials; P.g = g; P.lp = lp; P.tvec = tvec_edge;
   P.zero_row = tc->zero_row4; P.debug_acc = tc->debug_acc; P.error_flag = tc->error_flag; P.phase_cycles = tc->phase_cycles;
@@ -1105,18 +1125,20 @@ inline int launch(State* st, TcState* tc, int l, float* e, const float* uvab, fl
   P.lut_x = lut_x; P.cl = cl; P.lut = lut;
   P.n_tiles = (g.E + TC_TILE - 1) / TC_TILE;
   P.probe = tc->probe;
+  P.reverse = reverse;
   const int n_pairs = (P.n_tiles + 1) / 2;
   const int clusters = n_pairs < st->max_clusters ? n_pairs : st->max_clusters;
+
   const int mode = cl ? MODE_LUT : (P.gn_part ? MODE_GN : MODE_PLAIN);
   const int grid = 2 * clusters;
   if (agg_mode == AGG_MAX) {
-    if (mode == MODE_LUT) k_edge_layer_pair<true, MODE_LUT><<<grid, THREADS, SMEM_BYTES, stream>>>(st->wmap, tc->emap, P);
-    else if (mode == MODE_GN) k_edge_layer_pair<true, MODE_GN><<<grid, THREADS, SMEM_BYTES, stream>>>(st->wmap, tc->emap, P);
-    else k_edge_layer_pair<true, MODE_PLAIN><<<grid, THREADS, SMEM_BYTES, stream>>>(st->wmap, tc->emap, P);
+    if (mode == MODE_LUT) k_edge_layer_pair<true, MODE_LUT><<<grid, THREADS, SMEM_BYTES, stream>>>(st->wmap, tc->emap, st->smap, P);
+    else if (mode == MODE_GN) k_edge_layer_pair<true, MODE_GN><<<grid, THREADS, SMEM_BYTES, stream>>>(st->wmap, tc->emap, st->smap, P);
+    else k_edge_layer_pair<true, MODE_PLAIN><<<grid, THREADS, SMEM_BYTES, stream>>>(st->wmap, tc->emap, st->smap, P);
   } else {
-    if (mode == MODE_LUT) k_edge_layer_pair<false, MODE_LUT><<<grid, THREADS, SMEM_BYTES, stream>>>(st->wmap, tc->emap, P);
-    else if (mode == MODE_GN) k_edge_layer_pair<false, MODE_GN><<<grid, THREADS, SMEM_BYTES, stream>>>(st->wmap, tc->emap, P);
-    else k_edge_layer_pair<false, MODE_PLAIN><<<grid, THREADS, SMEM_BYTES, stream>>>(st->wmap, tc->emap, P);
+    if (mode == MODE_LUT) k_edge_layer_pair<false, MODE_LUT><<<grid, THREADS, SMEM_BYTES, stream>>>(st->wmap, tc->emap, st->smap, P);
+    else if (mode == MODE_GN) k_edge_layer_pair<false, MODE_GN><<<grid, THREADS, SMEM_BYTES, stream>>>(st->wmap, tc->emap, st->smap, P);
+    else k_edge_layer_pair<false, MODE_PLAIN><<<grid, THREADS, SMEM_BYTES, stream>>>(st->wmap, tc->emap, st->smap, P);
   }
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) {
