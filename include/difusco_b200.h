@@ -45,7 +45,9 @@ typedef struct dfb_ctx dfb_ctx;
 int dfb_abi_version(void);
 
 /* Create a context on CUDA device `device`.  Fails (DFB_E_CUDA) when no device is present:
- * there is no CPU fallback. */
+ * there is no CPU fallback.  The environment is read here and nowhere else (A/B switches, all default to the product
+ * path): DFB_GRAPH_CAPTURE=0 plain launches instead of the captured loop, DFB_PAIR_KERNEL=0 single-CTA edge kernel for
+ * every layer, DFB_SERPENTINE=0 every layer sweeps the edge stream upwards, DFB_TC_PROBE tuning-build counters. */
 int dfb_create(dfb_ctx** out, int device);
 int dfb_destroy(dfb_ctx* ctx);
 /* Message of the last failure on `ctx` (or of the last failed dfb_create when ctx == NULL). */
