@@ -749,6 +749,7 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
       // Segment structure of this warp's 32 rows.  With at most two node segments (every k-NN / ER workload: a 32-edge
       // group crosses at most one node boundary when degrees are >= 32) the reduce lane (column lane & 7, rows r_lo..r_lo+7)
       // needs one number: k0 = how many of its 8 rows belong to the first segment; prefix sums give both segment sums.
+      // (A kernel variant with only this path compiled in was slower: more spills under the 96-register cap.)
       const int r_lo = (lane >> 3) * 8;
       const bool fast = !MAXAGG && nseg <= 2 && nseg >= 1;
       int k0 = 8;
@@ -881,7 +882,7 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
         __syncwarp();                       // patch may be overwritten by the next gather
         if (step + 2 < 8) gather_issue(step + 2, gbuf0 + bo);
       };
-#pragma unroll 1
+#pragma unroll   // E1 / E2 / E3 fully unrolled: the step offsets fold into immediates (-3.8 % kernel time, fewer spills)
       for (int s2 = 0; s2 < 8; s2 += 2) {   // two steps per iteration: the buffer parity is static
         e1_step(s2, 0u);
         e1_step(s2 + 1, (uint32_t)GBUF);
@@ -921,7 +922,7 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
       {
         const float2 rs = splat2(rstd1), nm = splat2(-mean1 * rstd1);
         float2 S2p = splat2(0.f), Q2p = splat2(0.f);
-#pragma unroll 1
+#pragma unroll
         for (int c0 = cbase; c0 < cbase + 64; c0 += 16) {
           uint32_t v[16];
           tmem_ld16(t_acc1 + c0, v);
@@ -973,7 +974,7 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
       // ================= E3: s = silu(LN_O(e_til)) -> GEMM2 A operand, in place in TMEM =================
       // every 64-column K-chunk is produced cooperatively (part p converts columns [64 kc + 16 p, +16)), so chunk 0 is
       // complete after a quarter of E3 and GEMM2 runs underneath the rest
-#pragma unroll 1
+#pragma unroll
       for (int kc = 0; kc < 4; ++kc) {
         const int c0 = kc * 64 + part * 16;
         uint32_t v[16], w16[16];
