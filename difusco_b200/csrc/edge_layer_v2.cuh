@@ -35,6 +35,9 @@ namespace v2 {
 #define DFB_NA 5
 #define DFB_NB 4
 #endif
+// The kernel launches with 96 registers per thread (640 threads); the service warpgroup (warps 0..3) then shrinks to 32 and each
+// of the four worker warpgroups grows to 112 (setmaxnreg, 128 * 32 + 512 * 112 = 640 * 96): no spills in the worker code.
+constexpr int REGS_SERVICE = 32, REGS_WORKER = 112;
 constexpr int NA = DFB_NA, NB = DFB_NB;   // ring depths; NA + NB = 9 stages of 16 KB (tuning: -DDFB_NA=6 -DDFB_NB=3 measured no faster)
 constexpr int STAGE = 16384;                       // one fp32 box [128 rows x 32 cols] == bf16 hi (8 KB) | lo (8 KB)
 constexpr int HALF = 8192;
@@ -311,6 +314,7 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
 
   if (warp == 0) {
     // ===================================== weight TMA (both CTAs, each its N-half) =====================================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_SERVICE));
     if (lane == 0) {
       const int i_lo = LUT ? 8 : 0, n_use = debug ? 8 : 16;
       const uint64_t pol_keep = l2_policy_evict_last();
@@ -330,6 +334,7 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
     }
   } else if (warp == 1) {
     // ===================================== MMA issue (leader CTA only) =====================================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_SERVICE));
     if (leader && lane == 0) {
       uint32_t ub = 0, ga = 0;
 #ifdef DFB_PHASE_PROF
@@ -405,6 +410,7 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
     }
   } else if (warp == 2) {
     // ===================================== edge endpoints + input boxes =====================================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_SERVICE));
     uint32_t ga = 0;
     const uint64_t pol_stream = l2_policy_evict_first();
     for (int it = 0; it < n_my; ++it) {
@@ -446,10 +452,12 @@ k_edge_layer_pair(const __grid_constant__ CUtensorMap wmap, const __grid_constan
       __syncwarp();
     }
   } else if (warp == 3) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_SERVICE));
     // (no role: the workers issue their own result stores; the warp keeps the worker warps' ids congruent to their TMEM
     //  lane quarter)
   } else {
     // ===================================== row workers =====================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_WORKER));
     const int wq = warp & 3;                 // TMEM lane quarter this warp may access (hardware rule: warp id % 4)
     const int ww = warp - NSERV;             // 0..15 == part * 4 + wq
     const int part = ww >> 2;                // which 64-column slice of the row
