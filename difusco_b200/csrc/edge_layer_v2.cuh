@@ -5,23 +5,27 @@
 //   e_til = relu(LN_e(e_hat)) + tau                            :131,135,445
 //   e     = e + O silu(LN_O(e_til)) + b_O   (in place)         :449, :339-347
 //
-// What changed against edge_layer_tc.cuh (which stays for layer 0, the MIS last layer and the linear mode):
+// What changed against edge_layer_tc.cuh (which stays for the MIS last layer, graphs with more than MAXSEG node segments
+// per 32-edge group, the linear mode and as an A/B reference):
 //  * Two CTAs of a cluster work as ONE tensor-core unit: M = 256 (one 128-edge tile per CTA), N = 256, the weight
 //    operand B is split by output channel between the two CTAs (each CTA streams only HALF of C and O: the
 //    L2 -> SM weight traffic and the shared-memory footprint of B halve).  MMAs are issued by the leader CTA only;
 //    completion is multicast to both CTAs' mbarriers.
 //  * The fp32 edge tile comes in by TMA (32-column boxes, 128B swizzle) into the operand ring and is converted
-//    IN PLACE to the bf16 hi/lo K-major operand (64B swizzle): the round-1 kernel's register-staged global loads
-//    (30 % of all warp samples, long-scoreboard) are gone.
-//  * The operand rings (3 x 16 KB A, 3 x 16 KB B) no longer alias the gather / epilogue staging, so the phases of
-//    neighbouring tiles overlap: conversion + GEMM1 of tile t+1 run under E4 of tile t ("X phase"), the
-//    residual tile for E4 is fetched and the result stored by a dedicated I/O warp through a 3-box ring.
+//    IN PLACE and row-locally to the bf16 K-major operand (one 128B-swizzled tile per box: 32 hi | 32 lo values per row):
+//    the round-1 kernel's register-staged global loads (30 % of all warp samples, long-scoreboard) are gone.
+//  * The operand rings (NA x 16 KB A, NB x 16 KB B) do not alias the gather / epilogue staging, so the phases of
+//    neighbouring tiles overlap: conversion + GEMM1 of tile t+1 run under E4 of tile t ("X phase").  The residual is
+//    preloaded into GEMM2's accumulator (acc2 = e_in + b_O, GEMM2 accumulates), so E4 is a plain copy-out: every worker
+//    warp stages its 32 rows of a result box in its own gather buffers and issues the TMA store itself.
 //  * E1 takes all of its inputs (A h[col], V h[col], B h[row]) from warp-private cp.async staging that is
 //    filled two 8-column steps ahead; the segment-reduce patch reuses the staging buffer.
+//  * Layer 0 (input rows are one of two table rows) runs in LUT mode: no GEMM1, no input stream.  The last layer of the
+//    sparse TSP encoder accumulates the head's GroupNorm partial sums in its E4 (MODE_GN).
 //
 // Warp roles (640 threads): warp 0 weight TMA, warp 1 MMA issue + TMEM owner, warp 2 edge-index prefetch + input-box
-// TMA, warp 3 E4 residual loads / result stores, warps 4..19 row workers (thread == edge row == TMEM lane, the 256
-// channels of a row split over the 4 warps of a lane quarter).
+// TMA, warp 3 idle, warps 4..19 row workers (thread == edge row == TMEM lane, the 256 channels of a row split over the
+// 4 warps of a lane quarter).
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -47,7 +51,6 @@ constexpr int THREADS = (NSERV + NWORKW) * 32;     // 640
 constexpr int NWORK = NWORKW * 32;                 // 512
 constexpr int MAXSEG = 8;                          // node segments per 32-edge group the kernel stages B h[row] slots for
 constexpr int GBUF = 2048 + MAXSEG * 32;           // gather buffer: [32 rows][8 A | 8 V] fp32 + B-row slots x 32 B
-constexpr int PART_G = 4 * 2 * GBUF;               // the 8 gather buffers of one part (4 warps): also its E4 staging box
 constexpr int OFF_A = 0;
 constexpr int OFF_B = OFF_A + NA * STAGE;
 constexpr int OFF_G = OFF_B + NB * STAGE;
