@@ -23,8 +23,35 @@ try:   # in a Lightning environment stay a LightningModule so Trainer.test(model
   _Base = pl.LightningModule
 except Exception:   # pragma: no cover - Lightning is not in this image
   class _Base(torch.nn.Module):
-    def log(self, *a, **k):
-      pass
+    """Stand-in for LightningModule when Lightning is absent: `log` keeps running sums so that `logged_metrics()` gives
+    the epoch means Lightning's `on_epoch=True` reduction would report, and `sync_dist=True` (pl_tsp_model.py:253-255,
+    pl_mis_model.py:187-192) also averages over the ranks of an initialised process group."""
+
+    def log(self, name, value, prog_bar=False, on_step=None, on_epoch=None, sync_dist=False, **_):
+      acc = self.__dict__.setdefault("_dfb_logged", {})
+      s = acc.setdefault(name, [0.0, 0, False])
+      s[0] += float(value)
+      s[1] += 1
+      s[2] = s[2] or bool(sync_dist)
+
+    def logged_metrics(self, reset=False):
+      """{name: mean over the logged steps (and over ranks for sync_dist metrics)}; every rank must call it when a
+      process group is initialised and any metric was logged with sync_dist=True (it is a collective then)."""
+      import torch.distributed as dist
+      acc = self.__dict__.get("_dfb_logged", {})
+      out = {}
+      use_dist = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+      for name in sorted(acc):
+        total, count, sync = acc[name]
+        if sync and use_dist:
+          dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+          t = torch.tensor([total, float(count)], dtype=torch.float64, device=dev)
+          dist.all_reduce(t, op=dist.ReduceOp.SUM)
+          total, count = float(t[0]), float(t[1])
+        out[name] = total / max(count, 1)
+      if reset:
+        acc.clear()
+      return out
 
     @classmethod
     def load_from_checkpoint(cls, checkpoint_path, map_location=None, strict=True, **kwargs):

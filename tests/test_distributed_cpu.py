@@ -55,6 +55,15 @@ def _worker(rank, world, port, q):
     # more ranks than instances: the rank with the empty shard still joins the collectives (device / dtype explicit)
     one = denoise_sharded(inst[:1], run_batch, batch=2, device=torch.device("cpu"), dtype=torch.float32)
     ok = ok and len(one) == world and torch.equal(torch.cat(one), run_batch(inst[:1])) and one[-1].dtype == torch.float32
+    # sync_dist=True metric mean across ranks (pl_tsp_model.py:253-255) without Lightning
+    from difusco_b200.pl_meta_model import _Base
+    if hasattr(_Base, "logged_metrics"):
+      m = _Base()
+      for v in ([1.0, 3.0] if rank == 0 else [5.0, 7.0]):
+        m.log("test/solved_cost", v, on_epoch=True, sync_dist=True)
+      m.log("test/local_only", float(rank + 1))
+      got = m.logged_metrics()
+      ok = ok and abs(got["test/solved_cost"] - 4.0) < 1e-12 and abs(got["test/local_only"] - (rank + 1)) < 1e-12
     q.put((rank, bool(ok)))
   finally:
     dist.destroy_process_group()
