@@ -30,7 +30,7 @@ except Exception:   # pragma: no cover - Lightning is not in this image
     def log(self, name, value, prog_bar=False, on_step=None, on_epoch=None, sync_dist=False, **_):
       acc = self.__dict__.setdefault("_dfb_logged", {})
       s = acc.setdefault(name, [0.0, 0, False])
-      s[0] += float(value)
+      s[0] += float(value) if not hasattr(value, "__len__") else float(torch.as_tensor(value, dtype=torch.float64).mean())
       s[1] += 1
       s[2] = s[2] or bool(sync_dist)
 
